@@ -1,0 +1,274 @@
+"""ctypes binding of ``csrc/libccdec.so`` (C-ABI in ``include/ccdec.h``).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is present,
+loading / context creation raises ``RuntimeError``.  PyTorch tensors are only used as owners
+of device memory (``tensor.data_ptr()``) and of the CUDA stream.
+"""
+import ctypes
+import os
+import threading
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._desc import CCD_MAX_GRIDS, CcdCoolChicDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libccdec.so")
+
+CCD_OK = 0
+ERROR_NAMES = {
+    -1: "CCD_ERR_ARG", -2: "CCD_ERR_NN_TRUNCATED", -3: "CCD_ERR_DESYNC", -4: "CCD_ERR_UNSUPPORTED",
+    -5: "CCD_ERR_NOMEM", -6: "CCD_ERR_CUDA", -7: "CCD_ERR_NO_DEVICE",
+}
+
+EXPORTS = [
+    "ccd_version", "ccd_sizeof_desc", "ccd_last_error", "ccd_create", "ccd_destroy", "ccd_nn_count",
+    "ccd_latent_count", "ccd_decode_nn", "ccd_decode_many", "ccd_decode_coolchic", "ccd_decode_latents",
+    "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict",
+    "ccd_debug_laplace_domain", "ccd_last_timing",
+]
+
+
+class CcdJob(ctypes.Structure):
+    _fields_ = [
+        ("desc", ctypes.POINTER(CcdCoolChicDesc)),
+        ("nn_bytes", ctypes.c_char_p),
+        ("nn_nbytes", ctypes.c_size_t),
+        ("latent_bytes", ctypes.c_char_p),
+        ("latent_nbytes", ctypes.c_size_t),
+        ("d_out", ctypes.c_void_p),
+        ("d_latents", ctypes.c_void_p),
+        ("status", ctypes.c_int32),
+    ]
+
+
+class CcdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load libccdec.so (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C cool-chic_b200/csrc`).  There is no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, sz, i64, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64, ctypes.c_int
+        pd = ctypes.POINTER(CcdCoolChicDesc)
+        L.ccd_version.restype = ci
+        L.ccd_sizeof_desc.restype = ci
+        L.ccd_last_error.restype = ctypes.c_char_p
+        L.ccd_last_error.argtypes = [vp]
+        L.ccd_create.restype = ci
+        L.ccd_create.argtypes = [ci, ctypes.POINTER(vp)]
+        L.ccd_destroy.restype = None
+        L.ccd_destroy.argtypes = [vp]
+        L.ccd_nn_count.restype = i64
+        L.ccd_nn_count.argtypes = [pd]
+        L.ccd_latent_count.restype = i64
+        L.ccd_latent_count.argtypes = [pd, vp]
+        L.ccd_decode_nn.restype = i64
+        L.ccd_decode_nn.argtypes = [pd, ctypes.c_char_p, sz, vp, sz]
+        L.ccd_decode_many.restype = ci
+        L.ccd_decode_many.argtypes = [vp, ctypes.POINTER(CcdJob), ci, vp]
+        L.ccd_decode_coolchic.restype = ci
+        L.ccd_decode_coolchic.argtypes = [vp, pd, ctypes.c_char_p, sz, ctypes.c_char_p, sz, vp, vp, vp]
+        L.ccd_decode_latents.restype = ci
+        L.ccd_decode_latents.argtypes = [vp, pd, vp, ctypes.c_char_p, sz, vp, vp]
+        L.ccd_synthesize.restype = ci
+        L.ccd_synthesize.argtypes = [vp, pd, vp, vp, vp, vp]
+        L.ccd_encode_latents.restype = ci
+        L.ccd_encode_latents.argtypes = [vp, pd, vp, ci, ctypes.c_uint64, vp, vp, i64, vp, vp, vp]
+        L.ccd_finish_frame.restype = ci
+        L.ccd_finish_frame.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
+        L.ccd_inter_predict.restype = ci
+        L.ccd_inter_predict.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp]
+        L.ccd_debug_laplace_domain.restype = ci
+        L.ccd_debug_laplace_domain.argtypes = [vp, ci, ci, vp, vp]
+        L.ccd_last_timing.restype = ci
+        L.ccd_last_timing.argtypes = [vp, vp]
+        if L.ccd_sizeof_desc() != ctypes.sizeof(CcdCoolChicDesc):
+            raise RuntimeError("CcdCoolChicDesc layout mismatch between Python and libccdec.so")
+        _lib = L
+        return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != CCD_OK:
+        msg = load_library().ccd_last_error(None)
+        raise CcdError(rc, msg.decode() if msg else "")
+
+
+def decode_nn(desc: CcdCoolChicDesc, nn_bytes: bytes) -> np.ndarray:
+    """Host exp-Golomb decode of the NN payload -> int64 array (module/param order)."""
+    L = load_library()
+    n = L.ccd_nn_count(ctypes.byref(desc))
+    if n < 0:
+        _check(int(n))
+    out = np.zeros(int(n), dtype=np.int64)
+    got = L.ccd_decode_nn(ctypes.byref(desc), nn_bytes, len(nn_bytes), out.ctypes.data_as(ctypes.c_void_p), out.size)
+    if got < 0:
+        _check(int(got))
+    return out
+
+
+def latent_layout(desc: CcdCoolChicDesc):
+    L = load_library()
+    offs = (ctypes.c_int64 * CCD_MAX_GRIDS)()
+    n = L.ccd_latent_count(ctypes.byref(desc), offs)
+    if n < 0:
+        _check(int(n))
+    return int(n), [int(offs[i]) for i in range(desc.n_grids)]
+
+
+class Context:
+    """One decoder context per CUDA device (``ccd_create`` / ``ccd_destroy``)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("cool-chic_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        _check(self._lib.ccd_create(self.device, ctypes.byref(h)))
+        self._h = h
+        self.torch_device = torch.device("cuda", self.device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.ccd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
+
+    # ---- whole Cool-chic(s) -----------------------------------------------------------
+    def decode_many(self, descs: Sequence[CcdCoolChicDesc], nn_bytes: Sequence[bytes],
+                    latent_bytes: Sequence[bytes], want_latents: bool = False):
+        """Decode n independent Cool-chics concurrently.  Returns (outputs, latents) where
+        outputs[i] is a float32 CUDA tensor [1, C, H, W] (raw synthesis output)."""
+        n = len(descs)
+        jobs = (CcdJob * n)()
+        outs, lats = [], []
+        for i in range(n):
+            d = descs[i]
+            out = torch.empty((1, d.n_out_channels, d.img_h, d.img_w), dtype=torch.float32, device=self.torch_device)
+            outs.append(out)
+            jobs[i].desc = ctypes.pointer(d)
+            jobs[i].nn_bytes = nn_bytes[i]
+            jobs[i].nn_nbytes = len(nn_bytes[i])
+            jobs[i].latent_bytes = latent_bytes[i]
+            jobs[i].latent_nbytes = len(latent_bytes[i])
+            jobs[i].d_out = out.data_ptr()
+            if want_latents:
+                lat = torch.empty((d.n_symbols(),), dtype=torch.int8, device=self.torch_device)
+                lats.append(lat)
+                jobs[i].d_latents = lat.data_ptr()
+            else:
+                jobs[i].d_latents = None
+        rc = self._lib.ccd_decode_many(self._h, jobs, n, self._stream())
+        _check(rc)
+        return outs, (lats if want_latents else None)
+
+    def decode_coolchic(self, desc, nn_bytes: bytes, latent_bytes: bytes, want_latents: bool = False):
+        outs, lats = self.decode_many([desc], [nn_bytes], [latent_bytes], want_latents)
+        return (outs[0], lats[0]) if want_latents else outs[0]
+
+    # ---- stages -----------------------------------------------------------------------
+    def decode_latents(self, desc, nn_ints: np.ndarray, latent_bytes: bytes) -> torch.Tensor:
+        nn_ints = np.ascontiguousarray(nn_ints, dtype=np.int64)
+        lat = torch.empty((desc.n_symbols(),), dtype=torch.int8, device=self.torch_device)
+        _check(self._lib.ccd_decode_latents(self._h, ctypes.byref(desc), nn_ints.ctypes.data_as(ctypes.c_void_p),
+                                            latent_bytes, len(latent_bytes), lat.data_ptr(), self._stream()))
+        return lat
+
+    def synthesize(self, desc, nn_ints: np.ndarray, latents: torch.Tensor) -> torch.Tensor:
+        nn_ints = np.ascontiguousarray(nn_ints, dtype=np.int64)
+        assert latents.dtype == torch.int8 and latents.is_cuda and latents.is_contiguous()
+        out = torch.empty((1, desc.n_out_channels, desc.img_h, desc.img_w), dtype=torch.float32,
+                          device=self.torch_device)
+        _check(self._lib.ccd_synthesize(self._h, ctypes.byref(desc), nn_ints.ctypes.data_as(ctypes.c_void_p),
+                                        latents.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def encode_latents(self, desc, nn_ints: np.ndarray, latents: Optional[torch.Tensor] = None,
+                       seed: Optional[int] = None):
+        """Range-encode ``latents`` (mode 1) or draw them from the ARM with ``seed`` (mode 2).
+        Returns (latents int8 CUDA tensor, payload bytes, slow_path_count)."""
+        nn_ints = np.ascontiguousarray(nn_ints, dtype=np.int64)
+        n = desc.n_symbols()
+        if latents is None:
+            assert seed is not None
+            lat = torch.zeros((n,), dtype=torch.int8, device=self.torch_device)
+            mode = 2
+        else:
+            lat = latents.to(self.torch_device, torch.int8).contiguous().clone()
+            mode, seed = 1, 0
+        cap = n // 2 + 1024
+        words = torch.zeros((cap,), dtype=torch.int32, device=self.torch_device)
+        n_words = ctypes.c_int64(0)
+        slow = ctypes.c_int32(0)
+        _check(self._lib.ccd_encode_latents(self._h, ctypes.byref(desc), nn_ints.ctypes.data_as(ctypes.c_void_p),
+                                            mode, ctypes.c_uint64(seed), lat.data_ptr(), words.data_ptr(), cap,
+                                            ctypes.byref(n_words), ctypes.byref(slow), self._stream()))
+        payload = words[: n_words.value].cpu().numpy().astype("<u4").tobytes()
+        return lat, payload, int(slow.value)
+
+    def finish_frame(self, raw: torch.Tensor, bitdepth: int, frame_data_type: str):
+        """decode_frame tail: round / (420 average) / clamp / round.  raw: [1, 3, H, W] CUDA."""
+        assert raw.is_cuda and raw.dtype == torch.float32 and raw.dim() == 4 and raw.size(1) == 3
+        raw = raw.contiguous()
+        h, w = raw.shape[-2:]
+        code = {"rgb": 0, "yuv420": 1, "yuv444": 2}[frame_data_type]
+        if code == 1:
+            y = torch.empty((1, 1, h, w), dtype=torch.float32, device=raw.device)
+            u = torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=raw.device)
+            v = torch.empty_like(u)
+            _check(self._lib.ccd_finish_frame(self._h, raw.data_ptr(), h, w, bitdepth, code, y.data_ptr(),
+                                              u.data_ptr(), v.data_ptr(), self._stream()))
+            return {"y": y, "u": u, "v": v}
+        out = torch.empty_like(raw)
+        _check(self._lib.ccd_finish_frame(self._h, raw.data_ptr(), h, w, bitdepth, code, out.data_ptr(), None, None,
+                                          self._stream()))
+        return out
+
+    def last_timing(self):
+        ms = (ctypes.c_float * 4)()
+        _check(self._lib.ccd_last_timing(self._h, ms))
+        return {"entropy_ms": ms[0], "synthesis_ms": ms[1], "upload_ms": ms[2]}
+
+    def laplace_domain(self, sc_lo: int, sc_hi: int):
+        n = (sc_hi - sc_lo) * 32641
+        lo = np.zeros(n, dtype=np.uint32)
+        hi = np.zeros(n, dtype=np.uint32)
+        _check(self._lib.ccd_debug_laplace_domain(self._h, sc_lo, sc_hi, lo.ctypes.data_as(ctypes.c_void_p),
+                                                  hi.ctypes.data_as(ctypes.c_void_p)))
+        return lo, hi
+
+
+_contexts = {}
+
+
+def get_context(device: int = 0) -> Context:
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

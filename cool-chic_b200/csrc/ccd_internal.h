@@ -1,0 +1,102 @@
+// ccd_internal.h -- structures shared between the host API and the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ccdec.h"
+
+// --------------------------------------------------------------------------------------
+// Entropy stage (ccd_entropy.cu): one persistent CTA per Cool-chic stream.
+// --------------------------------------------------------------------------------------
+#define CCD_ENT_THREADS 512          // 15 producer warps + 1 range-coder warp
+#define CCD_ENT_WARPS (CCD_ENT_THREADS / 32)
+#define CCD_ENT_PRODUCERS (CCD_ENT_WARPS - 1)
+#define CCD_WIN 32                   // cumulative-window entries per symbol (31 decodable symbols)
+#define CCD_WIN_HALF 15              // window covers mu_int-15 .. mu_int+15
+#define CCD_ROW_COLS 64              // row ring: columns kept per row (power of 2)
+#define CCD_MAX_DIM 72               // n_ctx (<=40) + n_ifce_out (<=31)
+#define CCD_N_SCALE 2561
+#define CCD_MASK_STRIDE 10           // wavefront stride = ARM mask size 9 + 1 (latent.py:63,72)
+
+// One latent grid, in DECODE order (index 0 = coarsest = first decoded).
+struct EntGrid {
+    int32_t h, w;
+    int32_t n_diag;        // w + 10*(h-1), or h*w in raster mode
+    int32_t raster;        // w <= 9: plain raster scan (latent.py:113-122)
+    int64_t lat_off;       // offset of this grid in the latent array (decode order)
+    int32_t ifce_in;       // number of IFCE inputs (0: features are zero)
+    int32_t ifce_blob_off; // byte offset of this grid's IFCE parameters in the blob
+    int32_t ifce_blob_bytes;
+    int32_t n_dec;         // grids decoded before this one
+    // IFCE input channel c reads grid (this-1-c) at (yy >> sh, xx >> sh); sh < 0: constant 0
+    int32_t ch_w[31];
+    int32_t ch_sh[31];
+    int64_t ch_off[31];
+};
+
+struct EntStream {
+    int32_t n_grids;
+    int32_t n_ctx, cf, n_hidden, has_ifce;
+    int32_t ring;          // window ring entries (power of two)
+    int32_t rows;          // row ring rows (power of two)
+    int32_t mode;          // 0 decode, 1 encode given latents, 2 sample + encode
+    const uint32_t *words; // compressed words (device)
+    int64_t n_words;
+    int8_t *latents;       // device, decode order
+    int64_t n_symbols;
+    const unsigned char *blob; // device: ARM parameters followed by IFCE parameters
+    int32_t arm_blob_bytes;
+    int32_t ifce_blob_max;     // largest per-grid IFCE blob
+    int32_t *status;           // device: [0] error code, [1] words consumed, [2] slow-path count
+    uint64_t seed;
+    uint32_t *out_words;       // encode modes: output words (device)
+    int64_t out_cap;
+    EntGrid grid[CCD_MAX_GRIDS];
+};
+
+// Blob layouts ---------------------------------------------------------------------------
+// FAST (int32 operands, proven not to overflow by the host-side bound analysis):
+//   int32 Wh[n_hidden][dim][dimp]   (dimp = dim rounded up to 4; [in][out])
+//   int32 Wl[dim][2]                last layer
+//   int32 Ws[dim][2]                stabiliser (zeros if absent)
+//   (pad to 8 bytes)
+//   int64 Bh[n_hidden][dim], Bl[2], Bs[2]
+// IFCE arm (FAST): int32 W[n_in][cfp] (cfp = cf rounded up to 4), pad8, int64 B[cf]
+// GENERIC (all int64): W64h[n_hidden][dim][dim], Wl[dim][2], Ws[dim][2], Bh, Bl, Bs;
+//   IFCE: int64 W[n_in][cf], B[cf]
+
+struct EntLaunchCfg {
+    int n_ctx, cf;   // template selection
+    bool fast;
+    size_t smem_bytes;
+};
+
+int ccd_entropy_launch(const EntStream *d_streams, int n_streams, const EntLaunchCfg &cfg,
+                       const uint32_t *d_cdf, const float *d_scale, cudaStream_t st);
+size_t ccd_entropy_smem_bytes(int ring, int rows, int arm_blob_bytes, int ifce_blob_max);
+bool ccd_entropy_has_fast(int n_ctx, int cf);
+int ccd_cdf_table_build(uint32_t *d_cdf, const float *d_scale, cudaStream_t st);
+int ccd_laplace_domain(const float *d_scale, int sc_lo, int sc_hi, uint32_t *d_lo, uint32_t *d_hi,
+                       cudaStream_t st);
+
+// --------------------------------------------------------------------------------------
+// Synthesis stage (ccd_synth.cu)
+// --------------------------------------------------------------------------------------
+struct SynLayerDev {
+    int cin, cout, k, residual, relu;
+    const float *w; // [cout][cin][k][k]
+    const float *b; // [cout]
+};
+
+int ccd_ups_pre(const int8_t *d_lat, int h, int w, const float *w1d, int k, float *d_out, cudaStream_t st);
+int ccd_ups_first(const int8_t *d_lat, int h, int w, float *d_out, cudaStream_t st);
+int ccd_ups_convt(const float *d_in, int c, int h, int w, const float *w1d, int k, float *d_out, int ht,
+                  int wt, cudaStream_t st);
+int ccd_syn_layer(const float *d_in, int h, int w, const SynLayerDev &L, float *d_out, cudaStream_t st);
+int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, const SynLayerDev &L1,
+                       float *d_out, cudaStream_t st);
+int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st);
+int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st);
+int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, float *a, float *b, float *c,
+               cudaStream_t st);
