@@ -15,7 +15,8 @@ import torch
 from ._desc import CCD_MAX_GRIDS, CcdCoolChicDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libccdec.so")
+# CCD_LIB lets a developer load the instrumented build (csrc/libccdec_prof.so)
+LIB_PATH = os.environ.get("CCD_LIB") or os.path.join(_HERE, "csrc", "libccdec.so")
 
 CCD_OK = 0
 ERROR_NAMES = {
@@ -27,7 +28,7 @@ EXPORTS = [
     "ccd_version", "ccd_sizeof_desc", "ccd_last_error", "ccd_create", "ccd_destroy", "ccd_nn_count",
     "ccd_latent_count", "ccd_decode_nn", "ccd_decode_many", "ccd_decode_coolchic", "ccd_decode_latents",
     "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict",
-    "ccd_debug_laplace_domain", "ccd_last_timing",
+    "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_last_timing",
 ]
 
 
@@ -98,6 +99,8 @@ def load_library():
         L.ccd_inter_predict.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp]
         L.ccd_debug_laplace_domain.restype = ci
         L.ccd_debug_laplace_domain.argtypes = [vp, ci, ci, vp, vp]
+        L.ccd_debug_last_status.restype = ci
+        L.ccd_debug_last_status.argtypes = [vp, vp]
         L.ccd_last_timing.restype = ci
         L.ccd_last_timing.argtypes = [vp, vp]
         if L.ccd_sizeof_desc() != ctypes.sizeof(CcdCoolChicDesc):
@@ -255,6 +258,11 @@ class Context:
         ms = (ctypes.c_float * 4)()
         _check(self._lib.ccd_last_timing(self._h, ms))
         return {"entropy_ms": ms[0], "synthesis_ms": ms[1], "upload_ms": ms[2]}
+
+    def last_status(self):
+        st = (ctypes.c_int32 * 16)()
+        _check(self._lib.ccd_debug_last_status(self._h, st))
+        return list(st)
 
     def laplace_domain(self, sc_lo: int, sc_hi: int):
         n = (sc_hi - sc_lo) * 32641

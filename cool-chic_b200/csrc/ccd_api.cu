@@ -319,24 +319,31 @@ void pad_to(std::vector<unsigned char> &b, size_t a) {
 }
 
 void pack_arm(const ArmInts &a, bool fast, std::vector<unsigned char> &b) {
-    const int dim = a.dim, dimp = (dim + 3) & ~3;
+    const int dim = a.dim;
     if (fast) {
+        const int opm = (dim + 3) / 4, opmp = opm <= 2 ? 2 : (opm <= 4 ? 4 : 8), dimp = 4 * opm;
         for (int l = 0; l < a.n_hidden; l++)
             for (int i = 0; i < dim; i++)
-                for (int o = 0; o < dimp; o++) put_i32(b, o < dim ? a.W[l][(size_t)i * dim + o] : 0);
-        for (int i = 0; i < dim; i++)
-            for (int o = 0; o < 2; o++) put_i32(b, a.W[a.n_hidden][(size_t)i * 2 + o]);
-        for (int i = 0; i < dim; i++)
-            for (int o = 0; o < 2; o++) put_i32(b, a.Ws[(size_t)i * 2 + o]);
+                for (int m = 0; m < 4; m++)
+                    for (int o = 0; o < opmp; o++) {
+                        const int out = m * opm + o;
+                        put_i32(b, (o < opm && out < dim) ? a.W[l][(size_t)i * dim + out] : 0);
+                    }
+        for (int i = 0; i < dimp; i++)
+            for (int o = 0; o < 2; o++) put_i32(b, i < dim ? a.W[a.n_hidden][(size_t)i * 2 + o] : 0);
+        for (int i = 0; i < dimp; i++)
+            for (int o = 0; o < 2; o++) put_i32(b, i < dim ? a.Ws[(size_t)i * 2 + o] : 0);
         pad_to(b, 8);
+        for (int l = 0; l < a.n_hidden; l++)
+            for (int o = 0; o < dimp; o++) put_i64(b, o < dim ? a.B[l][o] : 0);
     } else {
         for (int l = 0; l < a.n_hidden; l++)
             for (size_t t = 0; t < (size_t)dim * dim; t++) put_i64(b, a.W[l][t]);
         for (size_t t = 0; t < (size_t)dim * 2; t++) put_i64(b, a.W[a.n_hidden][t]);
         for (size_t t = 0; t < (size_t)dim * 2; t++) put_i64(b, a.Ws[t]);
+        for (int l = 0; l < a.n_hidden; l++)
+            for (int o = 0; o < dim; o++) put_i64(b, a.B[l][o]);
     }
-    for (int l = 0; l < a.n_hidden; l++)
-        for (int o = 0; o < dim; o++) put_i64(b, a.B[l][o]);
     put_i64(b, a.B[a.n_hidden][0]);
     put_i64(b, a.B[a.n_hidden][1]);
     put_i64(b, a.Bs[0]);
@@ -398,6 +405,8 @@ struct CcdContext {
     size_t h_pin_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
+    int32_t last_status[16] = {0};
+    uint32_t prod_mask = 0x7777u;  // warps 3, 7, 11 stay idle: the coder warp (15) owns its scheduler
 };
 
 namespace {
@@ -814,7 +823,7 @@ int64_t ccd_decode_nn(const CcdCoolChicDesc *desc, const uint8_t *nn_bytes, size
 // stages: bit 0 entropy, bit 1 synthesis
 static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t *const *nn_ints, int stages,
                        const int8_t *const *d_lat_in, int mode, uint64_t seed, uint32_t *const *d_out_words,
-                       int64_t out_cap, int32_t (*statuses)[4], void *cuda_stream) {
+                       int64_t out_cap, int32_t (*statuses)[16], void *cuda_stream) {
     if (!ctx) return fail(CCD_ERR_ARG, "null context");
     if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(CCD_ERR_ARG, "bad job list");
     if (n_jobs == 0) return CCD_OK;
@@ -842,7 +851,7 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
         J.off_blob = up;
         up += al(J.blob.size());
         J.off_status = up;
-        up += al(16);
+        up += al(64);
         J.off_syn = up;
         up += al(J.syn_f.size() * 4);
         if (stages & 2) scratch_syn = std::max(scratch_syn, synthesis_scratch_bytes(J.d));
@@ -875,7 +884,7 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
         memset(h + J.off_words, 0, al(nbytes4 + 16));
         if (nbytes4) memcpy(h + J.off_words, jobs[i].latent_bytes, nbytes4);
         memcpy(h + J.off_blob, J.blob.data(), J.blob.size());
-        memset(h + J.off_status, 0, 16);
+        memset(h + J.off_status, 0, 64);
         if (!J.syn_f.empty()) memcpy(h + J.off_syn, J.syn_f.data(), J.syn_f.size() * 4);
         int8_t *lat = jobs[i].d_latents;
         if (!lat && d_lat_in && d_lat_in[i]) lat = const_cast<int8_t *>(d_lat_in[i]);
@@ -883,6 +892,7 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
         d_lat[(size_t)i] = lat;
         EntStream &S = J.es;
         S.mode = mode;
+        S.prod_mask = ctx->prod_mask;
         S.seed = seed + (uint64_t)i;
         S.words = reinterpret_cast<const uint32_t *>(dv + J.off_words);
         S.n_words = (int64_t)(nbytes4 / 4);
@@ -930,7 +940,7 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
     CUDA_TRY(cudaEventRecord(ctx->ev[3], st));
     // statuses back
     for (int i = 0; i < n_jobs; i++)
-        CUDA_TRY(cudaMemcpyAsync(h + P[(size_t)i].off_status, dv + P[(size_t)i].off_status, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h + P[(size_t)i].off_status, dv + P[(size_t)i].off_status, 64, cudaMemcpyDeviceToHost, st));
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) return fail(CCD_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(se));
     cudaEventElapsedTime(&ctx->last_ms[2], ctx->ev[0], ctx->ev[1]);
@@ -939,7 +949,8 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
     int first = CCD_OK;
     for (int i = 0; i < n_jobs; i++) {
         const int32_t *s = reinterpret_cast<const int32_t *>(h + P[(size_t)i].off_status);
-        if (statuses) memcpy(statuses[i], s, 16);
+        if (statuses) memcpy(statuses[i], s, 64);
+        memcpy(ctx->last_status, s, 64);
         if ((stages & 1) && s[0] != 0) {
             jobs[i].status = s[0];
             if (!first) first = fail(s[0], "job %d: corrupt latent payload (range decoder desynchronised)", i);
@@ -983,7 +994,7 @@ int ccd_encode_latents(CcdContext *ctx, const CcdCoolChicDesc *desc, const int64
     CcdJob j{desc, nullptr, 0, nullptr, 0, nullptr, d_latents, 0};
     const int64_t *nn[1] = {nn_ints};
     uint32_t *ow[1] = {d_out_words};
-    int32_t stt[1][4];
+    int32_t stt[1][16];
     int rc = decode_impl(ctx, &j, 1, nn, 1, nullptr, mode, seed, ow, out_cap_words, stt, cuda_stream);
     if (rc) return rc;
     if (n_words_out) *n_words_out = stt[0][3];
@@ -1018,6 +1029,18 @@ int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *ou
     if (ccd_laplace_domain(ctx->d_scale, sc_lo, sc_hi, lo, hi, 0)) return fail(CCD_ERR_CUDA, "launch failed");
     CUDA_TRY(cudaMemcpy(out_lo, lo, n * 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(out_hi, hi, n * 4, cudaMemcpyDeviceToHost));
+    return CCD_OK;
+}
+
+int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask) {
+    if (!ctx || (mask & 0x7fffu) == 0) return fail(CCD_ERR_ARG, "bad producer mask");
+    ctx->prod_mask = mask & 0x7fffu;
+    return CCD_OK;
+}
+
+int ccd_debug_last_status(const CcdContext *ctx, int32_t st[16]) {
+    if (!ctx || !st) return fail(CCD_ERR_ARG, "null pointer");
+    memcpy(st, ctx->last_status, 64);
     return CCD_OK;
 }
 

@@ -7,12 +7,12 @@
 //   rangecoder.py:87-94            (mu, scale) table lookup + constriction RangeDecoder.decode
 // with ONE persistent CTA per stream (a stream is a strict serial chain):
 //
-//   * 15 producer warps, one thread per symbol: wait until the symbol's left neighbour is
-//     decoded (shared-memory progress counter), gather the causal neighbourhood from a
-//     shared-memory row ring, evaluate IFCE + ARM in integer arithmetic (IMAD.WIDE, int32
-//     operands proven safe by the host, int64 accumulators), then fetch the symbol's
-//     32-entry cumulative window from the device-resident quantised-Laplace table and
-//     publish it in a shared-memory ring.
+//   * producer warps, a QUAD of lanes per symbol (8 symbols per warp): wait until the
+//     symbol's left neighbour is decoded (shared-memory progress counter), gather the causal
+//     neighbourhood from a shared-memory row ring, evaluate IFCE + ARM in integer arithmetic
+//     (IMAD.WIDE, int32 operands proven safe by the host, int64 accumulators, activations
+//     exchanged with quad shuffles), then fetch the symbol's 32-entry cumulative window from
+//     the device-resident quantised-Laplace table and publish it in a shared-memory ring.
 //   * 1 range-coder warp: each lane owns one candidate symbol of the window; the lane whose
 //     [scale*left, scale*left') interval contains (point - lower) wins (no division), the
 //     new state is broadcast with shuffles.  ~1 ballot + 4 shuffles per symbol.
@@ -24,7 +24,20 @@
 
 #include "ccd_internal.h"
 
+#ifdef CCD_PROFILE
+#define PROF_T(var) long long var = clock64()
+#define PROF_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(acc, t0)
+#endif
+
 namespace {
+
+struct ProfCounters {
+    long long wait = 0, arm = 0, win = 0, total = 0;
+    long long seg[6] = {0, 0, 0, 0, 0, 0};  // coder: per-segment cycles of the decode step
+};
 
 // context pattern: core/arm.py:496-562 (priority order over the 9x9 causal mask)
 __constant__ int8_t c_ctx_dy[40] = {0,  -1, -1, -1, 0,  -2, -3, 0,  -1, -2, -2, -1, -2, -1,
@@ -99,6 +112,12 @@ __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
     return ((uint64_t)hi << 32) | lo;
 }
 
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, mask);
+    uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), mask);
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // per-stream scalars, copied to registers once (EntStream lives in global memory)
 struct SLoc {
     int ring, rows, n_hidden, n_ctx, cf, mode;
@@ -107,31 +126,49 @@ struct SLoc {
     int64_t n_words;
     uint32_t *out_words;
     int64_t out_cap;
+    int32_t *status;
+    int64_t n_symbols;
 };
 
-__device__ __forceinline__ void st_shared_v4(uint4 *p, uint4 v) {
-    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((uint32_t)__cvta_generic_to_shared(p)),
-                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+// Shared-memory accessors by 32-bit shared-space address (explicit LDS/STS, never generic).
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
-__device__ __forceinline__ uint4 ld_shared_v4(const uint4 *p) {
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;
     asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"((uint32_t)__cvta_generic_to_shared(p))
+                 : "r"(a)
                  : "memory");
     return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds_s8(uint32_t a) {
+    int v;
+    asm volatile("ld.volatile.shared.s8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, int v) {
+    asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
 // shared memory carve-up -----------------------------------------------------------------
 struct SmemLayout {
-    uint32_t *ctrl;        // [0] progress (symbols decoded), [1] abort flag
+    uint32_t ctrl;         // shared address: [0] progress (symbols decoded)
     EntGrid *grid;         // current grid
     unsigned char *arm;    // ARM blob
     unsigned char *ifce;   // IFCE blob of the current grid
-    uint4 *meta;           // [ring]
-    uint32_t *win;         // [ring][32], 16B chunks XOR-swizzled by (slot & 7)
-    int8_t *rows;          // [rows][64]
+    uint32_t meta;         // shared address: uint4 [ring]
+    uint32_t win;          // shared address: u32 [ring][32]
+    uint32_t rows;         // shared address: int8 [rows][64]
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -139,8 +176,10 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int rows, int arm_bytes,
                                             int ifce_bytes) {
     SmemLayout L;
+    uint32_t base_a = (uint32_t)__cvta_generic_to_shared(base);
+    asm volatile("" : "+r"(base_a));  // opaque: keep it in a register instead of re-deriving it
     size_t p = 0;
-    L.ctrl = reinterpret_cast<uint32_t *>(base + p);
+    L.ctrl = base_a + (uint32_t)p;
     p += 64;
     L.grid = reinterpret_cast<EntGrid *>(base + p);
     p += align16(sizeof(EntGrid));
@@ -148,116 +187,150 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int r
     p += align16((size_t)arm_bytes);
     L.ifce = base + p;
     p += align16((size_t)ifce_bytes);
-    L.meta = reinterpret_cast<uint4 *>(base + p);
+    L.meta = base_a + (uint32_t)p;
     p += (size_t)ring * 16;
-    L.win = reinterpret_cast<uint32_t *>(base + p);
+    L.win = base_a + (uint32_t)p;
     p += (size_t)ring * CCD_WIN * 4;
-    L.rows = reinterpret_cast<int8_t *>(base + p);
+    L.rows = base_a + (uint32_t)p;
     (void)rows;
     return L;
 }
 
 // ---------------------------------------------------------------------------------------
-// ARM / IFCE evaluation (armint.py:180-203).  FAST: int32 operands, IMAD.WIDE.
+// ARM / IFCE evaluation (armint.py:180-203).
+// FAST path: int32 operands (proven safe by the host), int64 accumulators (IMAD.WIDE), and
+// each symbol is spread over a QUAD of lanes: member m owns activations [m*OPM, m*OPM+OPM).
+// One warp = 8 symbols.  This cuts the ARM latency ~8x w.r.t. one thread per symbol, which
+// is what bounds the short diagonals (the next diagonal cannot start before its ARM is done).
 template <int NCTX, int CF>
-struct FastArm {
+struct QuadArm {
     static constexpr int DIM = NCTX + CF;
-    static constexpr int DIMP = (DIM + 3) & ~3;
+    static constexpr int OPM = (DIM + 3) / 4;                       // activations per member
+    static constexpr int OPMP = OPM <= 2 ? 2 : (OPM <= 4 ? 4 : 8);  // padded for vector LDS
+    static constexpr int DIMP = 4 * OPM;
     static constexpr int CFP = (CF + 3) & ~3;
+    static_assert(OPM <= 8, "ARM too wide for the quad layout");
 
-    // IFCE features (component/coolchic.py:105-146) for the pixel (yy, xx) of the previous grid
-    static __device__ __forceinline__ void ifce(const EntGrid *g, const unsigned char *blob,
-                                                const int8_t *lat, int yy, int xx, int32_t *xf) {
-        if constexpr (CF > 0) {
-            const int n_in = g->ifce_in;
-            if (n_in == 0) {
-#pragma unroll
-                for (int f = 0; f < CF; f++) xf[f] = 0;
-                return;
-            }
-            const int32_t *W = reinterpret_cast<const int32_t *>(blob);
-            const long long *B =
-                reinterpret_cast<const long long *>(blob + (((size_t)n_in * CFP * 4 + 7) & ~(size_t)7));
-            long long acc[CF];
-#pragma unroll
-            for (int f = 0; f < CF; f++) acc[f] = B[f];
-            for (int c = 0; c < n_in; c++) {
-                int sh = g->ch_sh[c];
-                int v = 0;
-                if (sh >= 0) v = lat[g->ch_off[c] + (long long)(yy >> sh) * g->ch_w[c] + (xx >> sh)];
-                int xi = v << 16;
-#pragma unroll
-                for (int f4 = 0; f4 < CFP / 4; f4++) {
-                    int4 w = *reinterpret_cast<const int4 *>(W + c * CFP + f4 * 4);
-                    if (f4 * 4 + 0 < CF) acc[f4 * 4 + 0] += (long long)w.x * xi;
-                    if (f4 * 4 + 1 < CF) acc[f4 * 4 + 1] += (long long)w.y * xi;
-                    if (f4 * 4 + 2 < CF) acc[f4 * 4 + 2] += (long long)w.z * xi;
-                    if (f4 * 4 + 3 < CF) acc[f4 * 4 + 3] += (long long)w.w * xi;
-                }
-            }
-#pragma unroll
-            for (int f = 0; f < CF; f++) {
-                long long o = acc[f] >> 24;
-                // F.interpolate(ctx.to(torch.float)).to(int64): fp32 round trip (coolchic.py:142-144)
-                float fl = __ll2float_rn(o);
-                xf[f] = (int32_t)__float2ll_rz(fl);
-            }
+    static __device__ __forceinline__ void ld_w(const int32_t *p, int32_t (&w)[8]) {
+        if constexpr (OPMP == 2) {
+            int2 a = *reinterpret_cast<const int2 *>(p);
+            w[0] = a.x; w[1] = a.y;
+        } else if constexpr (OPMP == 4) {
+            int4 a = *reinterpret_cast<const int4 *>(p);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        } else {
+            int4 a = *reinterpret_cast<const int4 *>(p);
+            int4 b = *reinterpret_cast<const int4 *>(p + 4);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
         }
     }
 
-    // x: DIM context integers (latents, IFCE features with 8 fractional bits)
-    static __device__ __forceinline__ void arm(const unsigned char *blob, int n_hidden, int32_t (&x)[DIM],
-                                               long long &o0, long long &o1) {
-        const int32_t *Wh = reinterpret_cast<const int32_t *>(blob);
-        const int32_t *Wl = Wh + (size_t)n_hidden * DIM * DIMP;
-        const int32_t *Ws = Wl + DIM * 2;
-        size_t wbytes = ((size_t)(n_hidden * DIM * DIMP + DIM * 4) * 4 + 7) & ~(size_t)7;
-        const long long *Bh = reinterpret_cast<const long long *>(blob + wbytes);
-        const long long *Bl = Bh + (size_t)n_hidden * DIM;
-        const long long *Bs = Bl + 2;
+    // returns (mu, log-scale) in 1/256 units, identical on the 4 lanes of the quad
+    static __device__ __forceinline__ void run(const EntGrid *g, const unsigned char *arm_blob,
+                                               const unsigned char *ifce_blob, const int8_t *lat,
+                                               uint32_t rows, uint32_t row_mask, int n_hidden, int y, int x,
+                                               int m, long long &o0, long long &o1) {
+        const int w = g->w;
+        int32_t x0[OPM];
+        // ---- my share of the context: causal neighbours (latent.py:148-153) ...
 #pragma unroll
-        for (int i = 0; i < DIM; i++) x[i] <<= 16;
-        long long s0 = Bs[0], s1 = Bs[1];
-#pragma unroll
-        for (int i = 0; i < DIM; i++) {
-            int2 w = *reinterpret_cast<const int2 *>(Ws + 2 * i);
-            s0 += (long long)w.x * x[i];
-            s1 += (long long)w.y * x[i];
+        for (int o = 0; o < OPM; o++) {
+            const int i = m * OPM + o;
+            int v = 0;
+            if (i < NCTX) {
+                const int yy = y + c_ctx_dy[i], xx = x + c_ctx_dx[i];
+                if (yy >= 0 && xx >= 0 && xx < w)
+                    v = lds_s8(rows + ((((uint32_t)yy & row_mask) << 6) | ((uint32_t)xx & (CCD_ROW_COLS - 1))));
+            }
+            x0[o] = v;
         }
-        for (int l = 0; l < n_hidden; l++) {
-            long long acc[DIMP];
-            const long long *B = Bh + (size_t)l * DIM;
-            const int32_t *W = Wh + (size_t)l * DIM * DIMP;
+        // ---- ... and IFCE features (component/coolchic.py:105-146), evaluated at (y>>1, x>>1)
+        if constexpr (CF > 0) {
+            const int n_in = g->ifce_in;
+            if (n_in > 0 && (m + 1) * OPM > NCTX) {
+                const int32_t *W = reinterpret_cast<const int32_t *>(ifce_blob);
+                const long long *B =
+                    reinterpret_cast<const long long *>(ifce_blob + (((size_t)n_in * CFP * 4 + 7) & ~(size_t)7));
+                long long acc[OPM];
 #pragma unroll
-            for (int o = 0; o < DIMP; o++) acc[o] = (o < DIM) ? B[o] : 0;
+                for (int o = 0; o < OPM; o++) {
+                    const int f = m * OPM + o - NCTX;
+                    acc[o] = (f >= 0 && f < CF) ? B[f] : 0;
+                }
+                const int yy = y >> 1, xx = x >> 1;
+                for (int c = 0; c < n_in; c++) {
+                    const int sh = g->ch_sh[c];
+                    int v = 0;
+                    if (sh >= 0) v = lat[g->ch_off[c] + (long long)(yy >> sh) * g->ch_w[c] + (xx >> sh)];
+                    const int xi = v << 16;
 #pragma unroll
-            for (int i = 0; i < DIM; i++) {
-                const int xi = x[i];
+                    for (int o = 0; o < OPM; o++) {
+                        const int f = m * OPM + o - NCTX;
+                        if (f >= 0 && f < CF) acc[o] += (long long)W[c * CFP + f] * xi;
+                    }
+                }
 #pragma unroll
-                for (int o4 = 0; o4 < DIMP / 4; o4++) {
-                    int4 w = *reinterpret_cast<const int4 *>(W + i * DIMP + o4 * 4);
-                    acc[o4 * 4 + 0] += (long long)w.x * xi;
-                    acc[o4 * 4 + 1] += (long long)w.y * xi;
-                    acc[o4 * 4 + 2] += (long long)w.z * xi;
-                    acc[o4 * 4 + 3] += (long long)w.w * xi;
+                for (int o = 0; o < OPM; o++) {
+                    const int f = m * OPM + o - NCTX;
+                    if (f >= 0 && f < CF) {
+                        // F.interpolate(ctx.to(torch.float)).to(int64): fp32 round trip (coolchic.py:142-144)
+                        x0[o] = (int32_t)__float2ll_rz(__ll2float_rn(acc[o] >> 24));
+                    }
                 }
             }
+        }
+        // ---- MLP
+        const int32_t *Wh = reinterpret_cast<const int32_t *>(arm_blob);
+        const int32_t *Wl = Wh + (size_t)n_hidden * DIM * 4 * OPMP;
+        const int32_t *Ws = Wl + DIMP * 2;
+        const size_t wbytes = ((size_t)(n_hidden * DIM * 4 * OPMP + DIMP * 4) * 4 + 7) & ~(size_t)7;
+        const long long *Bh = reinterpret_cast<const long long *>(arm_blob + wbytes);
+        const long long *Bl = Bh + (size_t)n_hidden * DIMP;
+        int32_t xo[OPM];
 #pragma unroll
-            for (int o = 0; o < DIM; o++) {
+        for (int o = 0; o < OPM; o++) {
+            x0[o] <<= 16;
+            xo[o] = x0[o];
+        }
+        for (int l = 0; l < n_hidden; l++) {
+            long long acc[OPM];
+            const long long *B = Bh + (size_t)l * DIMP + m * OPM;
+#pragma unroll
+            for (int o = 0; o < OPM; o++) acc[o] = B[o];
+            const int32_t *W = Wh + ((size_t)l * DIM * 4 + m) * OPMP;
+#pragma unroll
+            for (int i = 0; i < DIM; i++) {
+                const int xi = __shfl_sync(0xffffffffu, xo[i % OPM], i / OPM, 4);
+                int32_t wv[8];
+                ld_w(W + (size_t)i * 4 * OPMP, wv);
+#pragma unroll
+                for (int o = 0; o < OPM; o++) acc[o] += (long long)wv[o] * xi;
+            }
+#pragma unroll
+            for (int o = 0; o < OPM; o++) {
                 long long a = acc[o];
                 a = a < 0 ? 0 : a;
-                x[o] = (int32_t)(a >> 16);
+                xo[o] = (int32_t)(a >> 16);
             }
         }
-        long long a0 = Bl[0], a1 = Bl[1];
+        // last layer (on the hidden state) + stabiliser (on the input): partial sums over my inputs
+        long long t0 = 0, t1 = 0;
 #pragma unroll
-        for (int i = 0; i < DIM; i++) {
-            int2 w = *reinterpret_cast<const int2 *>(Wl + 2 * i);
-            a0 += (long long)w.x * x[i];
-            a1 += (long long)w.y * x[i];
+        for (int o = 0; o < OPM; o++) {
+            const int i = m * OPM + o;
+            const int2 wl = *reinterpret_cast<const int2 *>(Wl + 2 * i);
+            const int2 ws = *reinterpret_cast<const int2 *>(Ws + 2 * i);
+            t0 += (long long)wl.x * xo[o] + (long long)ws.x * x0[o];
+            t1 += (long long)wl.y * xo[o] + (long long)ws.y * x0[o];
         }
-        o0 = (a0 + s0) >> 24;
-        o1 = (a1 + s1) >> 24;
+#pragma unroll
+        for (int d = 1; d < 4; d <<= 1) {
+            t0 += (long long)shfl_xor_u64((uint64_t)t0, d);
+            t1 += (long long)shfl_xor_u64((uint64_t)t1, d);
+        }
+        o0 = (t0 + Bl[0] + Bl[2]) >> 24;
+        o1 = (t1 + Bl[1] + Bl[3]) >> 24;
     }
 };
 
@@ -280,11 +353,7 @@ struct GenericArm {
             long long xi = v << 16;
             for (int f = 0; f < cf; f++) xf[f] += W[(size_t)c * cf + f] * xi;
         }
-        for (int f = 0; f < cf; f++) {
-            long long o = xf[f] >> 24;
-            float fl = __ll2float_rn(o);
-            xf[f] = __float2ll_rz(fl);
-        }
+        for (int f = 0; f < cf; f++) xf[f] = __float2ll_rz(__ll2float_rn(xf[f] >> 24));
     }
     static __device__ void arm(const unsigned char *blob, int dim, int n_hidden, long long *x, long long &o0,
                                long long &o1) {
@@ -323,15 +392,31 @@ struct GenericArm {
     }
 };
 
+// window chunk c (4 consecutive cumulatives) of a symbol: table entries + leak term + clamps
+__device__ __forceinline__ uint4 fix_window_chunk(uint4 v, int s_first) {
+    uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int s = s_first + q;
+        uint32_t l = e[q] + (uint32_t)(s - kSymMin);
+        l = (s <= kSymMin) ? 0u : l;
+        l = (s > kSymMax) ? (1u << 24) : l;
+        e[q] = l;
+    }
+    return make_uint4(e[0], e[1], e[2], e[3]);
+}
+
 // ---------------------------------------------------------------------------------------
-// Producer: symbols [c0, c0+32) of diagonal k.
+// Producer: symbols [c0, c0 + CHUNK) of diagonal k.  FAST: CHUNK = 8 (quad per symbol),
+// GENERIC: CHUNK = 32 (thread per symbol).
 template <int NCTX, int CF, bool FAST>
 __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &sm,
                                               const uint32_t *__restrict__ cdf, int lane, int y0, int x0,
                                               int n_k, int c0, uint32_t ord_diag, uint32_t ord_prev,
-                                              int y0_prev) {
+                                              int y0_prev, ProfCounters &pc) {
     const EntGrid *g = sm.grid;
-    const int i = c0 + lane;
+    const int member = FAST ? (lane & 3) : 0;
+    const int i = c0 + (FAST ? (lane >> 2) : lane);
     const bool valid = i < n_k;
     const int w = g->w;
     const int y = y0 + i;
@@ -342,48 +427,42 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
 
     // ---- dependencies: left neighbour decoded (and everything older), ring slot free
     uint32_t need;
-    if (g->raster) need = ord;                                  // everything before me
+    if (g->raster) need = ord;                                      // everything before me
     else if (x > 0) need = ord_prev + (uint32_t)(y - y0_prev) + 1u; // (y, x-1) sits on diagonal k-1
-    else need = ord_prev;                                        // first pixel of a row
-    uint32_t need_ring = ord + 1u - (uint32_t)S.ring;            // slot reuse: ord - ring consumed
+    else need = ord_prev;                                            // first pixel of a row
+    const uint32_t need_ring = ord + 1u - (uint32_t)S.ring;          // slot reuse: ord - ring consumed
     if ((int32_t)(need_ring - need) > 0) need = need_ring;
-    // warp-wide maximum (needs are increasing with the lane): one wait for the whole warp
+    // needs grow with the lane: one warp-wide wait on the maximum
     int32_t rel = valid ? (int32_t)(need - ord_diag) : INT32_MIN;
     rel = __reduce_max_sync(0xffffffffu, rel);
     need = ord_diag + (uint32_t)rel;
-    while ((int32_t)(ld_volatile_u32(&sm.ctrl[0]) - need) < 0) __nanosleep(32);
-    if (!valid) return;
-
-    // ---- gather the causal neighbourhood (latent.py:148-153), zero outside the grid
-    const int n_ctx = FAST ? NCTX : S.n_ctx;
-    const int cf = FAST ? CF : S.cf;
-    long long o0, o1;
-    if constexpr (FAST) {
-        int32_t xin[NCTX + CF];
-#pragma unroll
-        for (int t = 0; t < NCTX; t++) {
-            const int yy = y + c_ctx_dy[t], xx = x + c_ctx_dx[t];
-            int v = 0;
-            if (yy >= 0 && xx >= 0 && xx < w)
-                v = *reinterpret_cast<const volatile int8_t *>(
-                    &sm.rows[(((uint32_t)yy & row_mask) << 6) | ((uint32_t)xx & (CCD_ROW_COLS - 1))]);
-            xin[t] = v;
-        }
-        if constexpr (CF > 0) FastArm<NCTX, CF>::ifce(g, sm.ifce, S.latents, y >> 1, x >> 1, xin + NCTX);
-        FastArm<NCTX, CF>::arm(sm.arm, S.n_hidden, xin, o0, o1);
-    } else {
-        long long xin[CCD_MAX_DIM];
-        for (int t = 0; t < n_ctx; t++) {
-            const int yy = y + c_ctx_dy[t], xx = x + c_ctx_dx[t];
-            int v = 0;
-            if (yy >= 0 && xx >= 0 && xx < w)
-                v = *reinterpret_cast<const volatile int8_t *>(
-                    &sm.rows[(((uint32_t)yy & row_mask) << 6) | ((uint32_t)xx & (CCD_ROW_COLS - 1))]);
-            xin[t] = v;
-        }
-        if (cf > 0) GenericArm::ifce(g, sm.ifce, S.latents, cf, y >> 1, x >> 1, xin + n_ctx);
-        GenericArm::arm(sm.arm, n_ctx + cf, S.n_hidden, xin, o0, o1);
+    PROF_T(t0);
+    while ((int32_t)(lds_u32(sm.ctrl) - need) < 0) {
     }
+    PROF_ADD(pc.wait, t0);
+    PROF_T(t1);
+    long long o0 = 0, o1 = 0;
+    if constexpr (FAST) {
+        // all 32 lanes take part (quad shuffles); out-of-range symbols compute on clamped coordinates
+        const int yc = valid ? y : y0, xc = valid ? x : x0;
+        QuadArm<NCTX, CF>::run(g, sm.arm, sm.ifce, S.latents, sm.rows, row_mask, S.n_hidden, yc, xc, member, o0, o1);
+    } else {
+        if (valid) {
+            const int n_ctx = S.n_ctx, cf = S.cf;
+            long long xin[CCD_MAX_DIM];
+            for (int t = 0; t < n_ctx; t++) {
+                const int yy = y + c_ctx_dy[t], xx = x + c_ctx_dx[t];
+                int v = 0;
+                if (yy >= 0 && xx >= 0 && xx < w)
+                    v = lds_s8(sm.rows + ((((uint32_t)yy & row_mask) << 6) | ((uint32_t)xx & (CCD_ROW_COLS - 1))));
+                xin[t] = v;
+            }
+            if (cf > 0) GenericArm::ifce(g, sm.ifce, S.latents, cf, y >> 1, x >> 1, xin + n_ctx);
+            GenericArm::arm(sm.arm, n_ctx + cf, S.n_hidden, xin, o0, o1);
+        }
+    }
+    PROF_ADD(pc.arm, t1);
+    PROF_T(t2);
     // latent.py:165 + rangecoder.py:89-91 (np.take(..., mode="clip"))
     long long im = o0 + 16384, is = o1 + 1280;
     im = im < 0 ? 0 : (im > 32767 ? 32767 : im);
@@ -392,37 +471,43 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
     const int mu_int = ((mu_idx + 128) >> 8) - 64;
     const int fr = (mu_idx + 128) & 255;
     const int s_lo = mu_int - CCD_WIN_HALF;
-
     // ---- cumulative window: table row -> leak term + clamps -> shared ring
     const uint4 *row = reinterpret_cast<const uint4 *>(cdf + (((size_t)sc_idx << 8 | (size_t)fr) << 5));
-    uint4 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) v[c] = __ldg(row + c);
     const uint32_t slot = ord & ring_mask;
-    uint4 *wdst = reinterpret_cast<uint4 *>(sm.win + (size_t)slot * CCD_WIN);
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-        uint32_t e[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int s = s_lo + c * 4 + q;
-            uint32_t l = e[q] + (uint32_t)(s - kSymMin);
-            l = (s <= kSymMin) ? 0u : l;
-            l = (s > kSymMax) ? (1u << 24) : l;
-            e[q] = l;
+    const uint32_t wdst = sm.win + slot * (CCD_WIN * 4);
+    if constexpr (FAST) {
+        if (valid) {
+            const uint4 va = __ldg(row + 2 * member), vb = __ldg(row + 2 * member + 1);
+            sts_v4(wdst + 32u * member, fix_window_chunk(va, s_lo + 8 * member));
+            sts_v4(wdst + 32u * member + 16u, fix_window_chunk(vb, s_lo + 8 * member + 4));
         }
-        wdst[c ^ (slot & 7u)] = make_uint4(e[0], e[1], e[2], e[3]);
+        __threadfence_block();
+        __syncwarp();
+    } else {
+        if (valid) {
+            uint4 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) v[c] = __ldg(row + c);
+#pragma unroll
+            for (int c = 0; c < 8; c++) sts_v4(wdst + 16u * c, fix_window_chunk(v[c], s_lo + 4 * c));
+            __threadfence_block();
+        }
     }
-    __threadfence_block();
-    const uint32_t out_off = (uint32_t)(g->lat_off + (long long)y * w + x);
-    const uint32_t row_idx = (((uint32_t)y & row_mask) << 6) | ((uint32_t)x & (CCD_ROW_COLS - 1));
-    uint4 m = make_uint4(out_off, row_idx, (uint32_t)mu_idx | ((uint32_t)sc_idx << 16), ord + 1u);
-    st_shared_v4(&sm.meta[slot], m);
+    if (valid && member == 0) {
+        const uint32_t out_off = (uint32_t)(g->lat_off + (long long)y * w + x);
+        const uint32_t row_idx = (((uint32_t)y & row_mask) << 6) | ((uint32_t)x & (CCD_ROW_COLS - 1));
+        // meta: x = output offset, y = row-ring index | (s_lo + 128) << 16, z = mu_idx | sc_idx << 16, w = tag
+        sts_v4(sm.meta + slot * 16u, make_uint4(out_off, row_idx | ((uint32_t)(s_lo + 128) << 16),
+                                                (uint32_t)mu_idx | ((uint32_t)sc_idx << 16), ord + 1u));
+    }
+    PROF_ADD(pc.win, t2);
 }
 
 template <int NCTX, int CF, bool FAST>
-__device__ void producer_grid(const SLoc &S, const SmemLayout &sm, const uint32_t *__restrict__ cdf,
-                              int pwarp, int lane, uint32_t ord_grid, int &chunk_ctr) {
+__device__ __forceinline__ void producer_grid(const SLoc &S, const SmemLayout &sm, const uint32_t *__restrict__ cdf,
+                                           int prank, int n_prod, int lane, uint32_t ord_grid, int &chunk_ctr,
+                                           ProfCounters &pc) {
+    constexpr int CHUNK = FAST ? 8 : 32;
     const EntGrid *g = sm.grid;
     const int h = g->h, w = g->w, n_diag = g->n_diag, raster = g->raster;
     uint32_t ord = ord_grid, ord_prev = ord_grid;
@@ -443,10 +528,10 @@ __device__ void producer_grid(const SLoc &S, const SmemLayout &sm, const uint32_
             x0 = w - CCD_MASK_STRIDE + (r - (y0 - 1) * CCD_MASK_STRIDE);
             n_k = min(h - y0, x0 / CCD_MASK_STRIDE + 1);
         }
-        for (int c0 = 0; c0 < n_k; c0 += 32) {
-            if (chunk_ctr == pwarp)
-                produce_chunk<NCTX, CF, FAST>(S, sm, cdf, lane, y0, x0, n_k, c0, ord, ord_prev, y0_prev);
-            chunk_ctr = (chunk_ctr + 1 == CCD_ENT_PRODUCERS) ? 0 : chunk_ctr + 1;
+        for (int c0 = 0; c0 < n_k; c0 += CHUNK) {
+            if (chunk_ctr == prank)
+                produce_chunk<NCTX, CF, FAST>(S, sm, cdf, lane, y0, x0, n_k, c0, ord, ord_prev, y0_prev, pc);
+            chunk_ctr = (chunk_ctr + 1 == n_prod) ? 0 : chunk_ctr + 1;
         }
         ord_prev = ord;
         y0_prev = y0;
@@ -456,31 +541,47 @@ __device__ void producer_grid(const SLoc &S, const SmemLayout &sm, const uint32_
 
 // ---------------------------------------------------------------------------------------
 // Range-coder warp.  State: D = point - lower (mod 2^64), R = range.
-struct Coder {
-    uint64_t D, R;       // decoder: D = point - lower ; encoder: D = lower
-    int64_t wpos;        // next word index
-    uint32_t wcur, wnxt; // lane l holds word (chunk*32 + l) of the current / next 32-word chunk
-    uint32_t wnext;      // word[wpos], broadcast
+// (lower and point only ever appear through their difference, so one u64 replaces two.)
+struct Coder {          // range ENcoder state
+    uint64_t D, R;       // D = lower, R = range
     uint64_t prng;
-    int64_t nout;        // encoder: words emitted
-    uint32_t slow;       // slow-path count
-    int err;
+    int64_t nout;        // words emitted
+    uint32_t slow;       // symbols outside the window
 };
 
 __device__ __forceinline__ uint32_t load_word(const SLoc &S, int64_t i) {
     return (i < S.n_words) ? __ldg(S.words + i) : 0u;
 }
 
-__device__ __forceinline__ void coder_advance_word(const SLoc &S, Coder &c, int lane) {
-    c.wpos++;
-    if ((c.wpos & 31) == 0) {
-        c.wcur = c.wnxt;
-        c.wnxt = load_word(S, c.wpos + 32 + lane);
+// Exhaustive search with the exact f64 model for a symbol outside the 31-symbol window.
+// q: quantile (uniform).  Returns {l0, l1, src, sym}: per-lane cumulatives of the lane's
+// candidate in the winning round, the winning lane and the symbol.  (Returned in registers:
+// reference outputs would force the hot loop's variables into local memory.)
+__device__ __noinline__ uint4 slow_search(uint32_t q, int mu_idx, int sc_idx, const float *scale_tab, int lane) {
+    const double mu = (double)(mu_idx - 16384) * (1.0 / 256.0);
+    const double b = (double)scale_tab[sc_idx];
+    uint32_t ballot = 0, l0 = 0, l1 = 0;
+    int s = 0;
+    for (int r = 0; r < 4; r++) {
+        s = kSymMin + r * 32 + lane;
+        l0 = laplace_left_exact(s, mu, b);
+        l1 = laplace_left_exact(s + 1, mu, b);
+        ballot = __ballot_sync(0xffffffffu, l0 <= q && q < l1);
+        if (ballot) break;
     }
-    c.wnext = __shfl_sync(0xffffffffu, c.wcur, (int)(c.wpos & 31));
+    if (ballot == 0u) ballot = 1u;  // unreachable: left(-64) = 0 <= q < 2^24 = left(64)
+    const int src = __ffs(ballot) - 1;
+    const int sym = __shfl_sync(0xffffffffu, s, src);
+    return make_uint4(l0, l1, (uint32_t)src, (uint32_t)sym);
 }
 
-__device__ void encoder_emit(const SLoc &S, Coder &c, uint32_t L0, uint32_t L1, int lane) {
+__device__ __noinline__ uint2 exact_bounds(int sym, int mu_idx, int sc_idx, const float *scale_tab) {
+    const double mu = (double)(mu_idx - 16384) * (1.0 / 256.0);
+    const double b = (double)scale_tab[sc_idx];
+    return make_uint2(laplace_left_exact(sym, mu, b), laplace_left_exact(sym + 1, mu, b));
+}
+
+__device__ __noinline__ void encoder_emit(const SLoc &S, Coder &c, uint32_t L0, uint32_t L1, int lane) {
     const uint64_t scale = c.R >> 24;
     const uint64_t nl = c.D + scale * L0;
     const bool carry = nl < c.D;
@@ -505,116 +606,238 @@ __device__ void encoder_emit(const SLoc &S, Coder &c, uint32_t L0, uint32_t L1, 
     }
 }
 
-__device__ void coder_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
-                           int lane, uint32_t ord_begin, uint32_t ord_end, Coder &c) {
-    const uint32_t ring_mask = (uint32_t)S.ring - 1u;
-    const int mode = S.mode;
-    for (uint32_t j = ord_begin; j != ord_end; j++) {
-        const uint32_t slot = j & ring_mask;
-        uint4 m;
+struct SymIn {
+    uint4 m;      // x: output offset, y: row-ring index | (s_lo+128) << 16, z: mu_idx | sc_idx << 16, w: ordinal + 1
+    uint32_t L0;  // this lane's left cumulative (candidate symbol s_lo + lane)
+    uint32_t L1;  // the next lane's (lane 31: its own -> empty interval)
+};
+
+// Inputs of symbol j.  The window load is made ADDRESS-DEPENDENT on the tag load, so the
+// hardware cannot service it first: a valid tag implies a valid window (the producer writes
+// window -> fence -> tag).
+__device__ __forceinline__ void load_sym_meta(const SmemLayout &sm, uint32_t ring_mask, uint32_t j, SymIn &s) {
+    s.m = lds_v4(sm.meta + (j & ring_mask) * 16u);
+}
+__device__ __forceinline__ void load_sym_win(const SmemLayout &sm, uint32_t ring_mask, uint32_t j, uint32_t lane4,
+                                             SymIn &s) {
+    uint32_t a = sm.win + (j & ring_mask) * (CCD_WIN * 4) + lane4;
+    asm volatile("{\n .reg .b32 t;\n and.b32 t, %1, 0;\n add.u32 %0, %0, t;\n}\n" : "+r"(a) : "r"(s.m.w));
+    s.L0 = lds_u32(a);
+}
+__device__ __forceinline__ void load_sym(const SmemLayout &sm, uint32_t ring_mask, uint32_t j, uint32_t lane4,
+                                         SymIn &s) {
+    load_sym_meta(sm, ring_mask, j, s);
+    load_sym_win(sm, ring_mask, j, lane4, s);
+}
+
+// Publish the decoded symbol: row ring, global latent array, progress counter.  One
+// predicated store per instruction, no divergent branch on the coder's in-order stream.
+// The progress counter is written last (same lane as the row byte: program order).
+__device__ __forceinline__ void publish_symbol(int lane, uint32_t row_addr, int8_t *gptr, uint32_t ctrl_addr,
+                                               int sym, uint32_t progress) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p0, p1;\n"
+        " setp.eq.s32 p0, %0, 0;\n"
+        " setp.eq.s32 p1, %0, 1;\n"
+        " @p1 st.global.u8 [%3], %2;\n"
+        " @p0 st.volatile.shared.u8 [%1], %2;\n"
+        " @p0 st.volatile.shared.u32 [%4], %5;\n"
+        "}\n" ::"r"(lane),
+        "r"(row_addr), "r"(sym), "l"(gptr), "r"(ctrl_addr), "r"(progress)
+        : "memory");
+}
+
+// ---- decode.  Uniform state D, R in registers.
+struct DecState {
+    uint64_t D, R;        // D = point - lower (mod 2^64), R = range   
+    int64_t wpos;         // index of the next unread word
+    uint32_t wcur, wnxt;  // lane l holds word (32*chunk + l) of the current / next chunk
+    uint32_t wnext;       // word[wpos], broadcast
+    uint32_t slow;
+    int err;
+};
+
+__device__ __noinline__ void dec_advance_word(const SLoc &S, DecState &c, int lane) {
+    c.wpos++;
+    if ((c.wpos & 31) == 0) {
+        c.wcur = c.wnxt;
+        c.wnxt = load_word(S, c.wpos + 32 + lane);
+    }
+    c.wnext = __shfl_sync(0xffffffffu, c.wcur, (int)(c.wpos & 31));
+}
+
+// Serial chain of one symbol, `cur` validated.  Every lane owns one
+// candidate symbol [L0, L1); the lane whose scaled interval contains D wins (no division):
+// products -> compare -> vote -> bfind -> 4 shuffles.  Everything else is kept off that chain.
+__device__ __forceinline__ void decode_chain(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                             int lane, uint32_t j, const SymIn &cur, uint64_t &D, uint64_t &R,
+                                             uint32_t &wnext, DecState &c, ProfCounters &pc) {
+    const uint64_t scale = R >> 24;
+    const uint64_t P0 = scale * cur.L0, P1 = scale * cur.L1;
+    const uint64_t Dn = D - P0, Rn = P1 - P0;  // candidate new state of this lane
+    const uint32_t ballot = __ballot_sync(0xffffffffu, (P0 <= D) && (D < P1));
+    uint32_t usrc;
+    asm("bfind.u32 %0, %1;" : "=r"(usrc) : "r"(ballot));  // the single set bit (0xffffffff if none)
+    int src = (int)usrc;
+    uint64_t D2 = shfl_u64(Dn, src), R2 = shfl_u64(Rn, src);
+    int sym = (int)(cur.m.y >> 16) - 128 + src;
+    if (ballot == 0u) {
+        // no lane won: symbol outside the 31-symbol window, or corrupt stream
+        c.slow++;
+        uint64_t q = D / scale;
+        if (q >= (1ull << 24)) {
+            c.err = CCD_ERR_DESYNC;
+            q = (1ull << 24) - 1;
+        }
+        const uint4 r = slow_search((uint32_t)q, (int)(cur.m.z & 0xffffu), (int)(cur.m.z >> 16), scale_tab, lane);
+        src = (int)r.z;
+        sym = (int)r.w;
+        const uint64_t Q0 = scale * r.x, Q1 = scale * r.y;
+        D2 = shfl_u64(D - Q0, src);
+        R2 = shfl_u64(Q1 - Q0, src);
+    }
+    D = D2;
+    R = R2;
+    if ((R >> 32) == 0) {  // at most one renormalisation per symbol
+        R <<= 32;
+        D = (D << 32) | wnext;
+        dec_advance_word(S, c, lane);
+        wnext = c.wnext;
+    }
+    publish_symbol(lane, sm.rows + (cur.m.y & 0xffffu), S.latents + cur.m.x, sm.ctrl, sym, j + 1u);
+    (void)pc;
+}
+
+// One pipelined step.  The warp issues in order, so the statement order IS the schedule:
+//   L(j+2): request the inputs of symbol j+2 (LDS);
+//   V(j+1): validate symbol j+1 (loaded one step ago: no stall in the common case) and
+//           derive its upper bounds with one SHFL.DOWN;
+//   C(j)  : the serial chain of symbol j (products -> compare -> masked OR-reductions).
+__device__ __forceinline__ void decode_step3(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                             uint32_t ring_mask, int lane, uint32_t lane4, uint32_t j, SymIn &s0,
+                                             SymIn &s1, SymIn &s2, uint64_t &D, uint64_t &R, uint32_t &wnext,
+                                             DecState &c, ProfCounters &pc) {
+    load_sym(sm, ring_mask, j + 2u, lane4, s2);
+    // Readiness must be a warp-wide agreement: lanes may have loaded the tag at slightly
+    // different times, and the shuffle below needs every lane on the same side of the branch.
+    // Never BLOCK on symbol j+1 before symbol j is published: its producer may be waiting
+    // for symbol j (short diagonals, raster grids).
+    const bool ready = __all_sync(0xffffffffu, s1.m.w == j + 2u);
+    if (ready) s1.L1 = __shfl_down_sync(0xffffffffu, s1.L0, 1);
+    decode_chain(S, sm, scale_tab, lane, j, s0, D, R, wnext, c, pc);
+    if (!ready) {
+        PROF_T(t0);
         do {
-            m = ld_shared_v4(&sm.meta[slot]);
-        } while (m.w != j + 1u);
-        const uint32_t *wrow = sm.win + (size_t)slot * CCD_WIN;
-        const uint32_t sw = slot & 7u;
-        const int e1 = lane < 31 ? lane + 1 : lane;
-        const uint32_t L0 = ld_volatile_u32(wrow + ((((uint32_t)lane >> 2) ^ sw) << 2) + (lane & 3));
-        const uint32_t L1 = ld_volatile_u32(wrow + ((((uint32_t)e1 >> 2) ^ sw) << 2) + (e1 & 3));
-        const int mu_idx = (int)(m.z & 0xffffu), sc_idx = (int)(m.z >> 16);
-        const int s_lo = (((mu_idx + 128) >> 8) - 64) - CCD_WIN_HALF;
-        int sym;
-        if (mode == 0) {
-            // ------------------------------------------------------------ decode
-            const uint64_t scale = c.R >> 24;
-            uint64_t P0 = scale * L0, P1 = scale * L1;
-            bool win = (P0 <= c.D) && (c.D < P1);
-            uint32_t ballot = __ballot_sync(0xffffffffu, win);
-            int src;
-            if (ballot == 0u) {
-                // slow path: symbol outside the 31-symbol window (or corrupt stream)
-                c.slow++;
-                uint64_t q = c.D / scale;
-                if (q >= (1ull << 24)) {
-                    c.err = CCD_ERR_DESYNC;
-                    q = (1ull << 24) - 1;
-                }
-                const double mu = (double)(mu_idx - 16384) * (1.0 / 256.0);
-                const double b = (double)scale_tab[sc_idx];
-                uint32_t l0 = 0, l1 = 0;
-                int s = 0;
-                for (int r = 0; r < 4; r++) {
-                    s = kSymMin + r * 32 + lane;
-                    l0 = laplace_left_exact(s, mu, b);
-                    l1 = laplace_left_exact(s + 1, mu, b);
-                    ballot = __ballot_sync(0xffffffffu, l0 <= (uint32_t)q && (uint32_t)q < l1);
-                    if (ballot) break;
-                }
-                if (ballot == 0u) {  // cannot happen: left(-64)=0, left(64)=2^24 > q
-                    c.err = CCD_ERR_DESYNC;
-                    ballot = 1u;
-                }
-                src = __ffs(ballot) - 1;
-                sym = __shfl_sync(0xffffffffu, s, src);
-                P0 = scale * l0;
-                P1 = scale * l1;
-            } else {
+            load_sym(sm, ring_mask, j + 1u, lane4, s1);
+        } while (!__all_sync(0xffffffffu, s1.m.w == j + 2u));
+        PROF_ADD(pc.wait, t0);
+        s1.L1 = __shfl_down_sync(0xffffffffu, s1.L0, 1);
+    }
+}
+
+__device__ __forceinline__ void decode_step1(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                             uint32_t ring_mask, int lane, uint32_t lane4, uint32_t j, uint64_t &D,
+                                             uint64_t &R, uint32_t &wnext, DecState &c, ProfCounters &pc) {
+    SymIn s0;
+    PROF_T(t0);
+    do {
+        load_sym(sm, ring_mask, j, lane4, s0);
+    } while (!__all_sync(0xffffffffu, s0.m.w == j + 1u));
+    PROF_ADD(pc.wait, t0);
+    s0.L1 = __shfl_down_sync(0xffffffffu, s0.L0, 1);
+    decode_chain(S, sm, scale_tab, lane, j, s0, D, R, wnext, c, pc);
+}
+
+__device__ __forceinline__ void decode_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                            int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
+                                            ProfCounters &pc) {
+    const uint32_t ring_mask = (uint32_t)S.ring - 1u;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    uint64_t D = c.D, R = c.R;
+    uint32_t wnext = c.wnext;
+    uint32_t j = ord_begin;
+    if (ord_end - ord_begin > 8u) {
+        SymIn a, b, d;
+        do {
+            load_sym(sm, ring_mask, j, lane4, a);
+        } while (!__all_sync(0xffffffffu, a.m.w == j + 1u));
+        a.L1 = __shfl_down_sync(0xffffffffu, a.L0, 1);
+        load_sym(sm, ring_mask, j + 1u, lane4, b);
+        // three-buffer rotation, unrolled: no register moves between steps.  Steps touch
+        // symbols up to j+2, so stop 2 before the end of the grid.
+        const uint32_t stop = ord_end - 2u;
+        while (j + 3u <= stop) {
+            decode_step3(S, sm, scale_tab, ring_mask, lane, lane4, j, a, b, d, D, R, wnext, c, pc);
+            decode_step3(S, sm, scale_tab, ring_mask, lane, lane4, j + 1u, b, d, a, D, R, wnext, c, pc);
+            decode_step3(S, sm, scale_tab, ring_mask, lane, lane4, j + 2u, d, a, b, D, R, wnext, c, pc);
+            j += 3u;
+        }
+    }
+    for (; j < ord_end; j++) decode_step1(S, sm, scale_tab, ring_mask, lane, lane4, j, D, R, wnext, c, pc);
+    c.D = D;
+    c.R = R;
+    c.wnext = wnext;
+}
+
+// ---- encode (MODE 1: the latents given in S.latents; MODE 2: draw them from the model).
+// Not performance critical: used to fabricate synthetic streams.
+template <int MODE>
+__device__ __noinline__ void encode_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                         int lane, uint32_t ord_begin, uint32_t ord_end, Coder &c) {
+    const uint32_t ring_mask = (uint32_t)S.ring - 1u;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    for (uint32_t j = ord_begin; j != ord_end; j++) {
+        SymIn cur;
+        do {
+            load_sym(sm, ring_mask, j, lane4, cur);
+        } while (!__all_sync(0xffffffffu, cur.m.w == j + 1u));
+        const uint32_t L0 = cur.L0;
+        const uint32_t L1 = __shfl_down_sync(0xffffffffu, L0, 1);
+        const int mu_idx = (int)(cur.m.z & 0xffffu), sc_idx = (int)(cur.m.z >> 16);
+        const int s_lo = (int)(cur.m.y >> 16) - 128;
+        uint32_t l0, l1;
+        int src = -1, sym;
+        if constexpr (MODE == 2) {
+            const uint32_t q = (uint32_t)(splitmix64(c.prng) >> 40);
+            const uint32_t ballot = __ballot_sync(0xffffffffu, L0 <= q && q < L1);
+            if (ballot) {
                 src = __ffs(ballot) - 1;
                 sym = s_lo + src;
-            }
-            uint64_t Dn = c.D - P0, Rn = P1 - P0;
-            const bool rn = (Rn >> 32) == 0;
-            if (rn) {
-                Rn <<= 32;
-                Dn = (Dn << 32) | c.wnext;
-            }
-            const uint32_t rmask = __ballot_sync(0xffffffffu, rn);
-            c.D = shfl_u64(Dn, src);
-            c.R = shfl_u64(Rn, src);
-            if ((rmask >> src) & 1u) coder_advance_word(S, c, lane);
-        } else {
-            // ------------------------------------------------------------ encode / sample
-            uint32_t l0, l1;
-            int src = -1;
-            if (mode == 2) {
-                const uint32_t q = (uint32_t)(splitmix64(c.prng) >> 40);
-                uint32_t ballot = __ballot_sync(0xffffffffu, L0 <= q && q < L1);
-                if (ballot) {
-                    src = __ffs(ballot) - 1;
-                    sym = s_lo + src;
-                } else {
-                    const double mu = (double)(mu_idx - 16384) * (1.0 / 256.0);
-                    const double b = (double)scale_tab[sc_idx];
-                    int s = 0;
-                    for (int r = 0; r < 4; r++) {
-                        s = kSymMin + r * 32 + lane;
-                        ballot = __ballot_sync(0xffffffffu, laplace_left_exact(s, mu, b) <= q &&
-                                                                q < laplace_left_exact(s + 1, mu, b));
-                        if (ballot) break;
-                    }
-                    sym = __shfl_sync(0xffffffffu, s, __ffs(ballot) - 1);
-                }
-            } else {
-                sym = S.latents[m.x];
-                if (sym >= s_lo && sym < s_lo + 31) src = sym - s_lo;
-            }
-            if (src >= 0) {
                 l0 = __shfl_sync(0xffffffffu, L0, src);
                 l1 = __shfl_sync(0xffffffffu, L1, src);
             } else {
-                const double mu = (double)(mu_idx - 16384) * (1.0 / 256.0);
-                const double b = (double)scale_tab[sc_idx];
-                l0 = laplace_left_exact(sym, mu, b);
-                l1 = laplace_left_exact(sym + 1, mu, b);
                 c.slow++;
+                const uint4 r = slow_search(q, mu_idx, sc_idx, scale_tab, lane);
+                src = (int)r.z;
+                sym = (int)r.w;
+                l0 = __shfl_sync(0xffffffffu, r.x, src);
+                l1 = __shfl_sync(0xffffffffu, r.y, src);
             }
-            encoder_emit(S, c, l0, l1, lane);
+        } else {
+            sym = S.latents[cur.m.x];
+            if (sym >= s_lo && sym < s_lo + 31) {
+                src = sym - s_lo;
+                l0 = __shfl_sync(0xffffffffu, L0, src);
+                l1 = __shfl_sync(0xffffffffu, L1, src);
+            } else {
+                c.slow++;
+                const uint2 r = exact_bounds(sym, mu_idx, sc_idx, scale_tab);
+                l0 = r.x;
+                l1 = r.y;
+            }
         }
+        encoder_emit(S, c, l0, l1, lane);
         if (lane == 0) {
-            *reinterpret_cast<volatile int8_t *>(&sm.rows[m.y]) = (int8_t)sym;
-            S.latents[m.x] = (int8_t)sym;
-            st_volatile_u32(&sm.ctrl[0], j + 1u);
+            sts_u8(sm.rows + (cur.m.y & 0xffffu), sym);
+            S.latents[cur.m.x] = (int8_t)sym;
+            sts_u32(sm.ctrl, j + 1u);
         }
     }
+}
+
+__device__ __forceinline__ void named_barrier(int nthreads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -625,6 +848,17 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EntStream &G = streams[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // role assignment: the last warp is the range coder; producer warps are those enabled in
+    // prod_mask (by default the coder keeps its scheduler partition for itself)
+    const uint32_t prod_mask = G.prod_mask & ((1u << (CCD_ENT_WARPS - 1)) - 1u);
+    const bool is_coder = (warp == CCD_ENT_WARPS - 1);
+    const bool is_prod = !is_coder && ((prod_mask >> warp) & 1u);
+    if (!is_coder && !is_prod) return;
+    const int n_prod = __popc(prod_mask);
+    const int prank = __popc(prod_mask & ((1u << warp) - 1u));
+    const int n_active = (n_prod + 1) * 32;
+    const int atid = is_coder ? n_prod * 32 + lane : prank * 32 + lane;  // dense index among active threads
+
     SmemLayout sm = carve(smem_raw, G.ring, G.rows, G.arm_blob_bytes, G.ifce_blob_max);
     SLoc S;
     S.ring = G.ring;
@@ -638,56 +872,78 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     S.n_words = G.n_words;
     S.out_words = G.out_words;
     S.out_cap = G.out_cap;
+    S.status = G.status;
+    S.n_symbols = G.n_symbols;
 
     // one-time: control words, meta tags, ARM parameters
-    if (tid < 16) sm.ctrl[tid] = 0u;
-    for (int i = tid; i < S.ring; i += CCD_ENT_THREADS) sm.meta[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid * 4; i < G.arm_blob_bytes; i += CCD_ENT_THREADS * 4)
+    if (atid < 16) sts_u32(sm.ctrl + 4u * atid, 0u);
+    for (int i = atid; i < S.ring; i += n_active) sts_v4(sm.meta + 16u * i, make_uint4(0, 0, 0, 0));
+    for (int i = atid * 4; i < G.arm_blob_bytes; i += n_active * 4)
         *reinterpret_cast<uint32_t *>(sm.arm + i) = *reinterpret_cast<const uint32_t *>(G.blob + i);
 
-    const bool is_coder = (warp == CCD_ENT_WARPS - 1);
     Coder cd;
-    cd.err = 0;
     cd.slow = 0;
     cd.nout = 0;
     cd.prng = G.seed;
-    cd.wpos = 2;
-    cd.wcur = cd.wnxt = cd.wnext = 0;
-    if (is_coder) {
-        if (S.mode == 0) {
-            cd.wcur = load_word(S, lane);
-            cd.wnxt = load_word(S, 32 + lane);
-            const uint32_t w0 = __shfl_sync(0xffffffffu, cd.wcur, 0);
-            const uint32_t w1 = __shfl_sync(0xffffffffu, cd.wcur, 1);
-            cd.D = ((uint64_t)w0 << 32) | w1;
-            cd.wnext = __shfl_sync(0xffffffffu, cd.wcur, 2);
-        } else {
-            cd.D = 0;
-        }
-        cd.R = ~0ull;
+    cd.D = 0;
+    cd.R = ~0ull;
+    DecState ds;
+    ds.err = 0;
+    ds.slow = 0;
+    ds.wpos = 2;
+    ds.wcur = ds.wnxt = ds.wnext = 0;
+    ds.D = 0;
+    ds.R = ~0ull;
+    if (is_coder && S.mode == 0) {
+        ds.wcur = load_word(S, lane);
+        ds.wnxt = load_word(S, 32 + lane);
+        const uint32_t w0 = __shfl_sync(0xffffffffu, ds.wcur, 0);
+        const uint32_t w1 = __shfl_sync(0xffffffffu, ds.wcur, 1);
+        ds.D = ((uint64_t)w0 << 32) | w1;
+        ds.wnext = __shfl_sync(0xffffffffu, ds.wcur, 2);
     }
     uint32_t ord = 0;
     int chunk_ctr = 0;
+    ProfCounters pc;
     const int n_grids = G.n_grids;
     for (int gi = 0; gi < n_grids; gi++) {
-        __syncthreads();  // previous grid fully decoded, its latents visible CTA-wide
+        named_barrier(n_active);  // previous grid fully decoded, its latents visible CTA-wide
         {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&G.grid[gi]);
             uint32_t *dst = reinterpret_cast<uint32_t *>(sm.grid);
-            for (int i = tid; i < (int)(sizeof(EntGrid) / 4); i += CCD_ENT_THREADS) dst[i] = src[i];
+            for (int i = atid; i < (int)(sizeof(EntGrid) / 4); i += n_active) dst[i] = src[i];
             const EntGrid &Gg = G.grid[gi];
-            for (int i = tid * 4; i < Gg.ifce_blob_bytes; i += CCD_ENT_THREADS * 4)
+            for (int i = atid * 4; i < Gg.ifce_blob_bytes; i += n_active * 4)
                 *reinterpret_cast<uint32_t *>(sm.ifce + i) =
                     *reinterpret_cast<const uint32_t *>(G.blob + Gg.ifce_blob_off + i);
         }
-        __syncthreads();
+        named_barrier(n_active);
         const uint32_t n_sym = (uint32_t)sm.grid->h * (uint32_t)sm.grid->w;
-        if (is_coder)
-            coder_grid(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
-        else
-            producer_grid<NCTX, CF, FAST>(S, sm, cdf, warp, lane, ord, chunk_ctr);
+        PROF_T(tg);
+        if (is_coder) {
+            if (S.mode == 0) decode_grid(S, sm, scale_tab, lane, ord, ord + n_sym, ds, pc);
+            else if (S.mode == 1) encode_grid<1>(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
+            else encode_grid<2>(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
+        } else {
+            producer_grid<NCTX, CF, FAST>(S, sm, cdf, prank, n_prod, lane, ord, chunk_ctr, pc);
+        }
+        PROF_ADD(pc.total, tg);
         ord += n_sym;
     }
+#ifdef CCD_PROFILE
+    // [4] coder wait, [5] coder total, [6] producers wait, [7] arm, [8] window, [9] total (kilo-cycles, lane 0 of each warp)
+    if (lane == 0) {
+        if (is_coder) {
+            atomicAdd(&G.status[4], (int)(pc.wait >> 10));
+            atomicAdd(&G.status[5], (int)(pc.total >> 10));
+        } else {
+            atomicAdd(&G.status[6], (int)(pc.wait >> 10));
+            atomicAdd(&G.status[7], (int)(pc.arm >> 10));
+            atomicAdd(&G.status[8], (int)(pc.win >> 10));
+            atomicAdd(&G.status[9], (int)(pc.total >> 10));
+        }
+    }
+#endif
     if (is_coder) {
         if (S.mode != 0 && ord > 0) {
             // seal: point = lower + 2^32 - 1, emit its high word
@@ -709,9 +965,9 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
             cd.nout++;
         }
         if (lane == 0) {
-            G.status[0] = cd.err;
-            G.status[1] = (int32_t)cd.wpos;
-            G.status[2] = (int32_t)cd.slow;
+            G.status[0] = ds.err;
+            G.status[1] = (int32_t)ds.wpos;
+            G.status[2] = (int32_t)(ds.slow + cd.slow);
             G.status[3] = (int32_t)cd.nout;
         }
     }

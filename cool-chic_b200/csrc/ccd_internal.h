@@ -41,6 +41,7 @@ struct EntStream {
     int32_t ring;          // window ring entries (power of two)
     int32_t rows;          // row ring rows (power of two)
     int32_t mode;          // 0 decode, 1 encode given latents, 2 sample + encode
+    uint32_t prod_mask;    // which of warps 0..14 produce (warp 15 is the range coder)
     const uint32_t *words; // compressed words (device)
     int64_t n_words;
     int8_t *latents;       // device, decode order
@@ -56,12 +57,14 @@ struct EntStream {
 };
 
 // Blob layouts ---------------------------------------------------------------------------
-// FAST (int32 operands, proven not to overflow by the host-side bound analysis):
-//   int32 Wh[n_hidden][dim][dimp]   (dimp = dim rounded up to 4; [in][out])
-//   int32 Wl[dim][2]                last layer
-//   int32 Ws[dim][2]                stabiliser (zeros if absent)
+// FAST (int32 operands, proven not to overflow by the host-side bound analysis); a symbol is
+// evaluated by a quad of lanes, member m owning activations [m*opm, (m+1)*opm):
+//   opm = ceil(dim/4), opmp = 2|4|8 (opm padded for vector loads), dimp = 4*opm
+//   int32 Wh[n_hidden][dim][4][opmp]   weight of input i for the outputs of member m
+//   int32 Wl[dimp][2]                  last layer   (rows >= dim are zero)
+//   int32 Ws[dimp][2]                  stabiliser   (zeros if absent)
 //   (pad to 8 bytes)
-//   int64 Bh[n_hidden][dim], Bl[2], Bs[2]
+//   int64 Bh[n_hidden][dimp], Bl[2], Bs[2]
 // IFCE arm (FAST): int32 W[n_in][cfp] (cfp = cf rounded up to 4), pad8, int64 B[cf]
 // GENERIC (all int64): W64h[n_hidden][dim][dim], Wl[dim][2], Ws[dim][2], Bh, Bl, Bs;
 //   IFCE: int64 W[n_in][cf], B[cf]

@@ -171,6 +171,15 @@ int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_mo
 int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *out_lo,
                              uint32_t *out_hi);
 
+/* Tuning knob: which of warps 0..14 of the entropy CTA act as ARM producers (bit i = warp i;
+ * warp 15 is the range coder).  Default 0x7777: the coder keeps scheduler partition 3. */
+int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask);
+
+/* Entropy-kernel status words of the last job of the last call: [0] error, [1] words consumed,
+ * [2] slow-path symbols (outside the 31-symbol window), [3] words emitted (encode modes),
+ * [4..9] cycle counters when the library is built with -DCCD_PROFILE (else 0). */
+int ccd_debug_last_status(const CcdContext *ctx, int32_t st[16]);
+
 /* Timing of the last ccd_decode_many call on this context, measured with CUDA events on the
  * launching stream: ms[0] entropy stage, ms[1] upsampling+synthesis, ms[2] host prep + H2D. */
 int ccd_last_timing(const CcdContext *ctx, float ms[4]);
