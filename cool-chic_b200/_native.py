@@ -28,7 +28,7 @@ EXPORTS = [
     "ccd_version", "ccd_sizeof_desc", "ccd_last_error", "ccd_create", "ccd_destroy", "ccd_nn_count",
     "ccd_latent_count", "ccd_decode_nn", "ccd_decode_many", "ccd_decode_coolchic", "ccd_decode_latents",
     "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict",
-    "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_last_timing",
+    "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_debug_launch_count", "ccd_debug_set_producer_mask", "ccd_last_timing",
 ]
 
 
@@ -101,6 +101,10 @@ def load_library():
         L.ccd_debug_laplace_domain.argtypes = [vp, ci, ci, vp, vp]
         L.ccd_debug_last_status.restype = ci
         L.ccd_debug_last_status.argtypes = [vp, vp]
+        L.ccd_debug_launch_count.restype = ctypes.c_uint64
+        L.ccd_debug_launch_count.argtypes = []
+        L.ccd_debug_set_producer_mask.restype = ci
+        L.ccd_debug_set_producer_mask.argtypes = [vp, ctypes.c_uint32]
         L.ccd_last_timing.restype = ci
         L.ccd_last_timing.argtypes = [vp, vp]
         if L.ccd_sizeof_desc() != ctypes.sizeof(CcdCoolChicDesc):
@@ -254,10 +258,34 @@ class Context:
                                           self._stream()))
         return out
 
+    def inter_predict(self, residue, motion, refs, is_b, frame_data_type, global_flow, warp_filter_size):
+        """decode_frame P/B branch (bitstream/decode.py:156-189) -> pre-rounding frame [1,3,H,W]."""
+        h, w = residue.shape[-2:]
+        ref444 = []
+        for r in refs:
+            if frame_data_type == "yuv420":  # convert_420_to_444 (io/format/yuv.py:303-316): nearest x2
+                d = r.data
+                u = d["u"].repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+                v = d["v"].repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+                ref444.append(torch.cat((d["y"], u, v), dim=1).contiguous())
+            else:
+                ref444.append(r.data.contiguous())
+        out = torch.empty((1, 3, h, w), dtype=torch.float32, device=self.torch_device)
+        gf = (ctypes.c_int32 * 4)(*(list(global_flow) + [0, 0, 0, 0])[:4])
+        residue, motion = residue.contiguous(), motion.contiguous()
+        _check(self._lib.ccd_inter_predict(
+            self._h, residue.data_ptr(), motion.data_ptr(), ref444[0].data_ptr(),
+            ref444[1].data_ptr() if is_b else None, h, w, int(is_b), gf, int(warp_filter_size), out.data_ptr(),
+            self._stream()))
+        return out
+
     def last_timing(self):
         ms = (ctypes.c_float * 4)()
         _check(self._lib.ccd_last_timing(self._h, ms))
-        return {"entropy_ms": ms[0], "synthesis_ms": ms[1], "upload_ms": ms[2]}
+        return {"entropy_ms": ms[0], "synthesis_ms": ms[1], "upload_ms": ms[2], "upload_bytes": int(ms[3])}
+
+    def launch_count(self) -> int:
+        return int(self._lib.ccd_debug_launch_count())
 
     def last_status(self):
         st = (ctypes.c_int32 * 16)()

@@ -406,6 +406,7 @@ struct CcdContext {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms[4] = {0, 0, 0, 0};
     int32_t last_status[16] = {0};
+    uint64_t last_upload_bytes = 0;
     uint32_t prod_mask = 0x7777u;  // warps 3, 7, 11 stay idle: the coder warp (15) owns its scheduler
 };
 
@@ -905,6 +906,7 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
     for (int t = 0; t < n_jobs; t++)
         memcpy(h + off_streams + sizeof(EntStream) * (size_t)t, &P[(size_t)order[(size_t)t]].es, sizeof(EntStream));
     CUDA_TRY(cudaMemcpyAsync(dv, h, up, cudaMemcpyHostToDevice, st));
+    ctx->last_upload_bytes = up;
     CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
 
     if (stages & 1) {
@@ -1032,6 +1034,8 @@ int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *ou
     return CCD_OK;
 }
 
+uint64_t ccd_debug_launch_count(void) { return g_ccd_launches; }
+
 int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask) {
     if (!ctx || (mask & 0x7fffu) == 0) return fail(CCD_ERR_ARG, "bad producer mask");
     ctx->prod_mask = mask & 0x7fffu;
@@ -1047,6 +1051,7 @@ int ccd_debug_last_status(const CcdContext *ctx, int32_t st[16]) {
 int ccd_last_timing(const CcdContext *ctx, float ms[4]) {
     if (!ctx || !ms) return fail(CCD_ERR_ARG, "null pointer");
     memcpy(ms, ctx->last_ms, sizeof(float) * 4);
+    ms[3] = (float)ctx->last_upload_bytes;
     return CCD_OK;
 }
 

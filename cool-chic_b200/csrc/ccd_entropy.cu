@@ -980,10 +980,13 @@ int launch_t(const EntStream *d_streams, int n, size_t smem, const uint32_t *cdf
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<n, CCD_ENT_THREADS, smem, st>>>(d_streams, cdf, scale);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
 }  // namespace
+
+unsigned long long g_ccd_launches = 0;
 
 size_t ccd_entropy_smem_bytes(int ring, int rows, int arm_blob_bytes, int ifce_blob_max) {
     size_t p = 64 + align16(sizeof(EntGrid)) + align16((size_t)arm_blob_bytes) + align16((size_t)ifce_blob_max);

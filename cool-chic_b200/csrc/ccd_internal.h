@@ -69,6 +69,9 @@ struct EntStream {
 // GENERIC (all int64): W64h[n_hidden][dim][dim], Wl[dim][2], Ws[dim][2], Bh, Bl, Bs;
 //   IFCE: int64 W[n_in][cf], B[cf]
 
+// number of kernels launched by this library since load (bench.py reports it)
+extern unsigned long long g_ccd_launches;
+
 struct EntLaunchCfg {
     int n_ctx, cf;   // template selection
     bool fast;

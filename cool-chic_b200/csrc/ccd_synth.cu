@@ -199,23 +199,27 @@ K1d make_k1d(const float *w1d, int k) {
 int ccd_ups_first(const int8_t *d_lat, int h, int w, float *d_out, cudaStream_t st) {
     size_t n = (size_t)h * w;
     k_ups_first<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_lat, n, d_out);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
 int ccd_ups_pre(const int8_t *d_lat, int h, int w, const float *w1d, int k, float *d_out, cudaStream_t st) {
     k_ups_pre<<<grid2(w, h), kBlock2, 0, st>>>(d_lat, h, w, make_k1d(w1d, k), k, d_out);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
 int ccd_ups_convt(const float *d_in, int c, int h, int w, const float *w1d, int k, float *d_out, int ht,
                   int wt, cudaStream_t st) {
     k_ups_convt<<<grid2(wt, ht, c), kBlock2, 0, st>>>(d_in, h, w, make_k1d(w1d, k), k, d_out, ht, wt);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
 int ccd_syn_layer(const float *d_in, int h, int w, const SynLayerDev &L, float *d_out, cudaStream_t st) {
     k_syn_layer<<<grid2(w, h), kBlock2, 0, st>>>(d_in, h, w, L.cin, L.cout, L.k, L.residual, L.relu, L.w, L.b,
                                                  d_out);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
@@ -226,17 +230,20 @@ int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, c
     size_t smem = ((size_t)L0.cout * L0.cin + L0.cout + (size_t)L1.cout * L0.cout + L1.cout) * sizeof(float);
     k_syn_pw2<16, 8><<<(unsigned)((plane + 255) / 256), 256, smem, st>>>(
         d_in, plane, L0.cin, L0.cout, L1.cout, L0.relu, L1.relu, L0.w, L0.b, L1.w, L1.b, d_out);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
 int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st) {
     k_add<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_a, d_b, n);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
 int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st) {
     k_resize_nearest<<<grid2(W, H, c), kBlock2, 0, st>>>(d_in, h, w, d_out, H, W, (float)h / (float)H,
                                                          (float)w / (float)W);
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }
 
@@ -248,7 +255,11 @@ int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, flo
         k_finish_444<<<(unsigned)((3 * n + 255) / 256), 256, 0, st>>>(d_in, 3 * n, M, a);
     } else {
         k_finish_444<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_in, n, M, a);
-        if (h / 2 > 0 && w / 2 > 0) k_finish_420_uv<<<grid2(w / 2, h / 2, 2), kBlock2, 0, st>>>(d_in, h, w, M, b, c);
+        if (h / 2 > 0 && w / 2 > 0) {
+            k_finish_420_uv<<<grid2(w / 2, h / 2, 2), kBlock2, 0, st>>>(d_in, h, w, M, b, c);
+            g_ccd_launches++;
+        }
     }
+    g_ccd_launches++;
     return (int)cudaGetLastError();
 }

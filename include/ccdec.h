@@ -171,6 +171,9 @@ int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_mo
 int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *out_lo,
                              uint32_t *out_hi);
 
+/* Number of CUDA kernels this library has launched since it was loaded. */
+uint64_t ccd_debug_launch_count(void);
+
 /* Tuning knob: which of warps 0..14 of the entropy CTA act as ARM producers (bit i = warp i;
  * warp 15 is the range coder).  Default 0x7777: the coder keeps scheduler partition 3. */
 int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask);
@@ -181,7 +184,8 @@ int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask);
 int ccd_debug_last_status(const CcdContext *ctx, int32_t st[16]);
 
 /* Timing of the last ccd_decode_many call on this context, measured with CUDA events on the
- * launching stream: ms[0] entropy stage, ms[1] upsampling+synthesis, ms[2] host prep + H2D. */
+ * launching stream: ms[0] entropy stage, ms[1] upsampling+synthesis, ms[2] host prep + H2D;
+ * ms[3] = bytes uploaded host->device by that call (as a float). */
 int ccd_last_timing(const CcdContext *ctx, float ms[4]);
 
 #ifdef __cplusplus

@@ -28,6 +28,19 @@ static inline float scale_from_index(int idx) {
 
 int cco_sizeof_desc(void) { return (int)sizeof(CcoDesc); }
 
+/* The float tail is parallelised over output rows with OpenMP (results are independent of
+ * the thread count: every output keeps its own fixed summation order); the entropy stage
+ * of one stream is inherently serial.  cco_set_threads(0) = all cores. */
+#ifdef _OPENMP
+#include <omp.h>
+int cco_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int cco_set_threads(int n) { (void)n; return 1; }
+#endif
+
 /* ------------------------------------------------------------------------------------ */
 /* Context pattern: reference core/arm.py:496-562 (priority order over the 9x9 causal
  * mask; first n_ctx entries are used).  (dy, dx) relative to the coded pixel.          */
@@ -379,6 +392,21 @@ static inline uint32_t laplace_left(int s, double mu, double b) {
         c = 1.0 - 0.5 * exp((mu - x) / b);
     return (uint32_t)(k_free_weight * c) + (uint32_t)(s - SYM_MIN);
 }
+/* Host (libm) image of ccd_debug_laplace_domain: every |d| = n/256, n in [0, 32641), for the
+ * scales [sc_lo, sc_hi): trunc(FW*0.5*exp(-|d|/b)) and trunc(FW*(1-0.5*exp(-|d|/b))). */
+void cco_laplace_domain(int sc_lo, int sc_hi, uint32_t *lo, uint32_t *hi) {
+    const int ND = 32641;
+    for (int sc = sc_lo; sc < sc_hi; sc++) {
+        double b = (double)scale_from_index(sc);
+        for (int n = 0; n < ND; n++) {
+            double d = (double)n * (1.0 / 256.0);
+            size_t i = (size_t)(sc - sc_lo) * ND + (size_t)n;
+            lo[i] = (uint32_t)(k_free_weight * (0.5 * exp(-d / b)));
+            hi[i] = (n == 0) ? lo[i] : (uint32_t)(k_free_weight * (1.0 - 0.5 * exp(-d / b)));
+        }
+    }
+}
+
 uint32_t cco_laplace_left(int s, float mu, float scale) {
     return laplace_left(s, (double)mu, (double)scale);
 }
@@ -791,6 +819,7 @@ static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ?
 static void convt_kron(const float *in, int h, int w, const float *w1d, int k, float *out, int ht,
                        int wt) {
     int P0 = k / 2, C = 2 * P0 - 1 + k / 2;
+#pragma omp parallel for schedule(static)
     for (int u = 0; u < ht; u++) {
         int o1 = u + C;
         int i1_lo = (o1 - (k - 1) + 1) / 2; /* ceil((o1-k+1)/2), o1-k+1 >= 0 here */
@@ -820,6 +849,7 @@ static void convt_kron(const float *in, int h, int w, const float *w1d, int k, f
 /* hi = conv2d(x, kron(w,w), zero padding k/2) + x  (upsampling.py:189-196) */
 static void preconcat_kron(const float *in, int h, int w, const float *w1d, int k, float *out) {
     int p = k / 2;
+#pragma omp parallel for schedule(static)
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
             float acc = 0.0f;
@@ -848,6 +878,7 @@ static void expand_sym(const float *par, int k, float *full) {
 static void syn_conv(const float *in, int cin, int h, int w, const float *wt, const float *bias,
                      int cout, int k, int residual, int relu, float *out) {
     int p = (k - 1) / 2;
+#pragma omp parallel for collapse(2) schedule(static)
     for (int co = 0; co < cout; co++)
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {

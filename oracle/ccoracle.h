@@ -68,6 +68,7 @@ enum {
 };
 
 int cco_sizeof_desc(void);
+int cco_set_threads(int n); /* returns the number of threads the float tail will use */
 
 /* number of NN integers transmitted: counts[m*2+wb] with m in arm,ifce,ups,syn. */
 int64_t cco_nn_counts(const CcoDesc *d, int64_t counts[8]);
@@ -123,6 +124,7 @@ void *cco_rc_dec_new(const uint32_t *words, size_t n);
 void cco_rc_dec_free(void *h);
 int cco_rc_decode_block(void *h, const float *mu, const float *scale, int n, int32_t *out);
 uint32_t cco_laplace_left(int s, float mu, float scale);
+void cco_laplace_domain(int sc_lo, int sc_hi, uint32_t *lo, uint32_t *hi);
 
 #ifdef __cplusplus
 }

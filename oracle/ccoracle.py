@@ -31,6 +31,8 @@ def lib():
         L = ctypes.CDLL(_SO)
         vp, sz, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64
         L.cco_sizeof_desc.restype = ctypes.c_int
+        L.cco_set_threads.restype = ctypes.c_int
+        L.cco_set_threads.argtypes = [ctypes.c_int]
         L.cco_nn_counts.restype = i64
         L.cco_nn_counts.argtypes = [vp, vp]
         L.cco_decode_nn.restype = i64
@@ -52,6 +54,8 @@ def lib():
         L.cco_inter_predict.restype = ctypes.c_int
         L.cco_inter_predict.argtypes = [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp,
                                         ctypes.c_int, vp]
+        L.cco_laplace_domain.restype = None
+        L.cco_laplace_domain.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp]
         L.cco_laplace_left.restype = ctypes.c_uint32
         L.cco_laplace_left.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float]
         _lib = L
@@ -159,3 +163,16 @@ def finish_frame(x: np.ndarray, bitdepth: int, data_type: str):
     a = np.zeros((3, h, w), np.float32)
     _chk(lib().cco_finish_frame(_p(x), h, w, bitdepth, code, _p(a), None, None), "finish_frame")
     return a
+
+
+def laplace_domain(sc_lo: int, sc_hi: int):
+    n = (sc_hi - sc_lo) * 32641
+    lo = np.zeros(n, dtype=np.uint32)
+    hi = np.zeros(n, dtype=np.uint32)
+    lib().cco_laplace_domain(sc_lo, sc_hi, _p(lo), _p(hi))
+    return lo, hi
+
+
+def set_threads(n: int = 0) -> int:
+    """Threads used by the float tail (0 = leave as is / all cores); returns the count."""
+    return int(lib().cco_set_threads(n))

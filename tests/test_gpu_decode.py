@@ -1,0 +1,241 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle and the
+golden fixtures.  Integer work (NN ints, latents, payload bytes) must be bit-exact; the
+float path is bit-exact against the oracle (same canonical fp32 order) and within the
+north-star tolerance 1e-5 of the PyTorch reference."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+TOL_FLOAT = 1e-5
+
+
+def _decode_ref(oracle, desc, nn, payload):
+    lat, _ = oracle.decode_latents(desc, nn, payload)
+    return lat
+
+
+# ------------------------------------------------------------------------------------------
+def test_kodim14_through_c_abi(ctx, oracle, kodim14):
+    import torch
+
+    d = kodim14["desc"]
+    out, lat = ctx.decode_coolchic(d, kodim14["nn_bytes"], kodim14["lat_bytes"], want_latents=True)
+    torch.cuda.synchronize()
+    assert ctx.last_status()[:3] == [0, 7739, 0]  # no error, 7738 words + 1 over-read, no slow path
+    assert np.array_equal(lat.cpu().numpy(), kodim14["latents"])  # bit-exact vs the reference
+    nn = oracle.decode_nn(d, kodim14["nn_bytes"])
+    raw_o = oracle.synthesize(d, nn, kodim14["latents"])
+    raw = out[0].cpu().numpy()
+    assert np.array_equal(raw, raw_o)  # same canonical fp32 order as the oracle
+    g = kodim14["raw_rows"]
+    assert np.abs(raw[:, g["rows"], :] - g["data"]).max() <= TOL_FLOAT  # vs the PyTorch reference
+    img = ctx.finish_frame(out, 8, "rgb")[0].cpu().numpy()
+    assert np.array_equal(img, oracle.finish_frame(raw_o, 8, "rgb"))
+    u8 = np.round(img * 255).astype(np.uint8).transpose(1, 2, 0)
+    diff = u8.astype(np.int32) - kodim14["image"].astype(np.int32)
+    assert np.abs(diff).max() <= 1 and int((diff != 0).sum()) <= 32  # rounding ties only
+
+
+def test_decode_video_api_and_cli(ctx, kodim14, tmp_path):
+    from coolchic_b200.bitstream.decode import decode_frame, decode_video
+    from coolchic_b200.io import FrameData
+
+    path = os.path.join(GOLDEN, "kodim14.cool")
+    frames = decode_video(path, decoded_path=str(tmp_path / "out.ppm"))
+    assert list(frames) == ["0"] and isinstance(frames["0"], FrameData)
+    fd = frames["0"]
+    assert (fd.bitdepth, fd.frame_data_type, fd.img_size) == (8, "rgb", (512, 768))
+    assert fd.data.device.type == "cpu" and fd.data.dtype.is_floating_point and tuple(fd.data.shape) == (1, 3, 512, 768)
+    u8 = np.round(fd.data[0].numpy() * 255).astype(np.uint8).transpose(1, 2, 0)
+    assert int((u8 != kodim14["image"]).sum()) <= 32
+    raw = (tmp_path / "out.ppm").read_bytes()
+    assert raw.startswith(b"P6\n768 512\n255\n") and np.array_equal(
+        np.frombuffer(raw[len(b"P6\n768 512\n255\n"):], dtype=np.uint8).reshape(512, 768, 3), u8)
+    # decode_frame returns the unread tail (decode.py:212)
+    frame, rest = decode_frame(kodim14["data"][8:] + b"tail", reference_frames=[])
+    assert rest == b"tail" and frame.img_size == (512, 768)
+    # the command line
+    out_png = tmp_path / "cli.png"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "cc_decode.py"), "-i", path, "-o", str(out_png)],
+                       capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr
+    assert "Decoding frame 0" in r.stdout and "seconds." in r.stdout
+    from PIL import Image
+
+    assert np.array_equal(np.asarray(Image.open(out_png)), u8)
+
+
+def test_corrupt_payload_is_reported(ctx, kodim14):
+    from coolchic_b200 import _native
+
+    bad = bytearray(kodim14["lat_bytes"])
+    bad[0:64] = b"\xff" * 64
+    with pytest.raises(_native.CcdError) as e:
+        ctx.decode_coolchic(kodim14["desc"], kodim14["nn_bytes"], bytes(bad))
+    assert e.value.code == -3  # CCD_ERR_DESYNC
+    with pytest.raises(_native.CcdError) as e:
+        ctx.decode_coolchic(kodim14["desc"], kodim14["nn_bytes"][:500], kodim14["lat_bytes"])
+    assert e.value.code == -2  # CCD_ERR_NN_TRUNCATED
+    # an empty payload decodes like the reference does (missing words read as 0): no crash
+    ctx.decode_coolchic(kodim14["desc"], kodim14["nn_bytes"], b"")
+
+
+def test_device_range_encoder_and_sampler(ctx, oracle, kodim14):
+    import torch
+
+    d = kodim14["desc"]
+    nn = oracle.decode_nn(d, kodim14["nn_bytes"])
+    _, payload, slow = ctx.encode_latents(d, nn, latents=torch.from_numpy(kodim14["latents"]).cuda())
+    assert payload == kodim14["lat_bytes"] and slow == 0  # byte-exact with real constriction output
+    lat_s, payload_s, _ = ctx.encode_latents(d, nn, seed=77)
+    lat_o, payload_o = oracle.sample_latents(d, nn, 77)
+    assert np.array_equal(lat_s.cpu().numpy(), lat_o) and payload_s == payload_o
+    # the sampled stream leaves the 31-symbol window often: exercises the exact-CDF slow path
+    dec = ctx.decode_latents(d, nn, payload_s)
+    assert np.array_equal(dec.cpu().numpy(), lat_o) and ctx.last_status()[2] > 1000
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic streams: (H, W), latent_resolution, hyperlatent_resolution, header overrides
+CASES = [
+    ((64, 96), (0, 6), (4, 6), {}),                     # same structure as the sample, tiny
+    ((17, 33), (0, 4), None, {}),                       # odd sizes, ceil grids, crops
+    ((129, 7), (0, 3), None, {}),                       # w <= 9: raster scan on every grid
+    ((40, 250), (0, 6), (4, 6), {}),                    # coarse grids 1 pixel high
+    ((96, 64), (0, 2), None, {}),                       # few grids
+    ((1, 1), (0, 1), None, {}),                         # degenerate
+    ((72, 88), (2, 5), None, {"final_upsampling_type": "nearest"}),  # motion-like: nearest x4 output
+    ((60, 100), (0, 6), (4, 6), {"spatial_context_arm": 8}),          # no template: generic int64 kernel
+    ((60, 100), (0, 5), None, {"spatial_context_arm": 20}),           # vhop ARM width (20 + 6)
+    ((48, 80), (0, 4), None, {"n_hidden_layers_arm": 1, "linear_stabiliser_arm": 0}),
+    ((48, 80), (0, 4), None, {"output_feature_ifce": 0}),             # no IFCE at all -> generic
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0][0]}x{c[0][1]}-{i}" for i, c in enumerate(CASES)])
+def test_synthetic_stream_parity(ctx, oracle, seed_stream, case):
+    import torch
+
+    from coolchic_b200 import synth
+    from coolchic_b200._desc import desc_from_header
+
+    hw, lr, hr, ov = case
+    ov = dict(ov)
+    fut = ov.pop("final_upsampling_type", None)
+    if ov.get("output_feature_ifce", 1) == 0:
+        ov["ifce_resolution"] = None
+    cc_bytes, header, lat_dev = synth.make_coolchic(ctx, seed_stream, hw, lr, hr, seed=3, final_upsampling_type=fut,
+                                                    overrides=ov)
+    if ov.get("output_feature_ifce", 1) == 0:
+        assert header.get_value("ifce_resolution") is None
+    h2 = type(header)()
+    rest = h2.read_header(cc_bytes)
+    d = desc_from_header(h2)
+    n_nn, n_lat = h2.get_value("nn_n_bytes"), h2.get_value("n_bytes_latent")
+    nn_bytes, payload = rest[:n_nn], rest[n_nn:n_nn + n_lat]
+    nn = oracle.decode_nn(d, nn_bytes)
+    lat_in = lat_dev.cpu().numpy()
+    # encoder parity: the device payload is the oracle's payload
+    assert payload == oracle.encode_latents(d, nn, lat_in)
+    # decoder parity
+    out, lat = ctx.decode_coolchic(d, nn_bytes, payload, want_latents=True)
+    torch.cuda.synchronize()
+    assert ctx.last_status()[0] == 0
+    assert np.array_equal(lat.cpu().numpy(), lat_in)                       # round trip
+    assert np.array_equal(lat.cpu().numpy(), _decode_ref(oracle, d, nn, payload))  # vs oracle
+    assert np.array_equal(out[0].cpu().numpy(), oracle.synthesize(d, nn, lat_in))  # bit-exact float tail
+    assert tuple(out.shape) == (1, 3, hw[0], hw[1])
+
+
+def test_many_streams_concurrently(ctx, oracle, seed_stream):
+    """decode_many: one persistent CTA per stream, mixed architectures in one call."""
+    import torch
+
+    from coolchic_b200 import synth
+    from coolchic_b200._desc import desc_from_header
+
+    items = []
+    for i in range(9):
+        hw = (48 + 8 * i, 120 - 4 * i)
+        ov = {"spatial_context_arm": 8} if i % 4 == 3 else {}
+        cc_bytes, header, lat_dev = synth.make_coolchic(ctx, seed_stream, hw, (0, 5), (4, 5) if i % 2 else None,
+                                                        seed=10 + i, overrides=ov)
+        h2 = type(header)()
+        rest = h2.read_header(cc_bytes)
+        items.append((desc_from_header(h2), rest[:h2.get_value("nn_n_bytes")],
+                      rest[h2.get_value("nn_n_bytes"):][:h2.get_value("n_bytes_latent")], lat_dev.cpu().numpy()))
+    outs, lats = ctx.decode_many([x[0] for x in items], [x[1] for x in items], [x[2] for x in items], want_latents=True)
+    torch.cuda.synchronize()
+    for (d, nnb, _, lat_in), out, lat in zip(items, outs, lats):
+        assert np.array_equal(lat.cpu().numpy(), lat_in)
+        assert np.array_equal(out[0].cpu().numpy(), oracle.synthesize(d, oracle.decode_nn(d, nnb), lat_in))
+
+
+@pytest.mark.parametrize("fmt,bitdepth", [("rgb", 8), ("yuv444", 10), ("yuv420", 8), ("yuv420", 10), ("yuv420", 12)])
+def test_finish_frame(ctx, oracle, fmt, bitdepth):
+    import torch
+
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-0.3, 1.3, size=(3, 37, 50)).astype(np.float32)
+    # exact ties of the rounding grid as well
+    x[0, 0, :8] = (np.arange(8) + 0.5) / (2**bitdepth - 1)
+    got = ctx.finish_frame(torch.from_numpy(x[None]).cuda(), bitdepth, fmt)
+    want = oracle.finish_frame(x, bitdepth, fmt)
+    if fmt == "yuv420":
+        for k in "yuv":
+            assert np.array_equal(got[k][0, 0].cpu().numpy(), want[k])
+    else:
+        assert np.array_equal(got[0].cpu().numpy(), want)
+
+
+def test_laplace_cdf_device_equals_host_exhaustively(ctx, oracle):
+    """the only platform-dependent operation of the entropy model is
+    the f64 exp().  Its argument set is finite (32641 numerators x 2561 scales, both CDF
+    branches): the device evaluation must equal the host libm one on ALL of it."""
+    bad = 0
+    step = 128
+    for sc in range(0, 2561, step):
+        hi_sc = min(2561, sc + step)
+        dlo, dhi = ctx.laplace_domain(sc, hi_sc)
+        hlo, hhi = oracle.laplace_domain(sc, hi_sc)
+        bad += int((dlo != hlo).sum()) + int((dhi != hhi).sum())
+    assert bad == 0
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties (round trip, payload idempotence) + oracle latents
+@pytest.mark.parametrize("hw,lr", [((1080, 1920), (0, 6)), ((2160, 3840), (0, 7))], ids=["1080p-7grids", "4k-8grids"])
+def test_full_size_round_trip(ctx, oracle, seed_stream, hw, lr):
+    import torch
+
+    from coolchic_b200 import synth
+    from coolchic_b200._desc import desc_from_header
+
+    cc_bytes, header, lat_dev = synth.make_coolchic(ctx, seed_stream, hw, lr, None, seed=1)
+    h2 = type(header)()
+    rest = h2.read_header(cc_bytes)
+    d = desc_from_header(h2)
+    nn_bytes = rest[:h2.get_value("nn_n_bytes")]
+    payload = rest[h2.get_value("nn_n_bytes"):][:h2.get_value("n_bytes_latent")]
+    assert d.n_symbols() == {1080: 2764710, 2160: 11059110}[hw[0]]
+    out, lat = ctx.decode_coolchic(d, nn_bytes, payload, want_latents=True)
+    torch.cuda.synchronize()
+    st = ctx.last_status()
+    assert st[0] == 0 and st[1] == len(payload) // 4 + 1  # every word consumed, one over-read
+    assert torch.equal(lat, lat_dev)                       # encode -> decode round trip
+    nn = oracle.decode_nn(d, nn_bytes)
+    # re-encoding the decoded latents reproduces the payload (idempotence)
+    _, payload2, _ = ctx.encode_latents(d, nn, latents=lat)
+    assert payload2 == payload
+    assert torch.isfinite(out).all()
+    if hw[0] == 1080:  # the oracle needs ~1.5 s for these latents; 4K is covered by the round trip
+        assert np.array_equal(lat.cpu().numpy(), _decode_ref(oracle, d, nn, payload))
+        # float tail on a crop-free subset: compare a few rows against the oracle's full run is too slow
+        # (9 s); checksum of checksums instead: per-channel sums are finite and non-trivial
+        s = out.double().sum(dim=(2, 3)).cpu().numpy()
+        assert np.all(np.abs(s) > 1.0)
