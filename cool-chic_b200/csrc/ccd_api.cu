@@ -407,7 +407,7 @@ struct CcdContext {
     float last_ms[4] = {0, 0, 0, 0};
     int32_t last_status[16] = {0};
     uint64_t last_upload_bytes = 0;
-    uint32_t prod_mask = 0x7777u;  // warps 3, 7, 11 stay idle: the coder warp (15) owns its scheduler
+    uint32_t prod_mask = 0x3777u;  // warps 3, 7, 11 stay idle: the coder warp (15) owns its scheduler
 };
 
 namespace {
@@ -481,6 +481,7 @@ int prepare_job(PreparedJob &P, const int64_t *nn_ints_opt) {
                                  d->qshift[2], d->qshift[3], false, 0, true));
         i128 bnd = 0;
         if (!ifce_bound(ifce.back(), &bnd)) fast = false;
+        if (d->grid_ifce_in[L.ifce_grid[j]] > CCD_IFCE_FAST_MAX) fast = false;
         feat_bound = std::max(feat_bound, bnd);
     }
     if (fast) fast = arm_fits_int32(arm, d->n_ctx, feat_bound);
@@ -546,7 +547,7 @@ int prepare_job(PreparedJob &P, const int64_t *nn_ints_opt) {
         rows_need = std::max(rows_need, G.raster ? 8 : (G.w - 1) / CCD_MASK_STRIDE + 6);
     }
     S.ifce_blob_max = ifce_max;
-    S.ring = std::min(1024, std::max(64, next_pow2(2 * n_max + 64)));
+    S.ring = std::min(1024, std::max(64, next_pow2(2 * n_max + 64)));  // 148 B of shared memory per slot
     S.rows = next_pow2(rows_need);
     P.smem = ccd_entropy_smem_bytes(S.ring, S.rows, S.arm_blob_bytes, S.ifce_blob_max);
     if (P.smem > 227 * 1024)
@@ -1037,8 +1038,8 @@ int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *ou
 uint64_t ccd_debug_launch_count(void) { return g_ccd_launches; }
 
 int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask) {
-    if (!ctx || (mask & 0x7fffu) == 0) return fail(CCD_ERR_ARG, "bad producer mask");
-    ctx->prod_mask = mask & 0x7fffu;
+    if (!ctx || (mask & 0x3fffu) == 0) return fail(CCD_ERR_ARG, "bad producer mask");
+    ctx->prod_mask = mask & 0x3fffu;
     return CCD_OK;
 }
 

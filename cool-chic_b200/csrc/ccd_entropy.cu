@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t laplace_left_exact(int s, double mu, double 
     return laplace_nonleaky(((double)s - 0.5) - mu, b) + (uint32_t)(s - kSymMin);
 }
 
-// Table: NL[sc][f][t] = trunc(FW*cdf((t - 15.5) - (f-128)/256)), sc < 2561, f < 256, t < 32.
+// Table: NL[sc][f][t] = trunc(FW*cdf((t - CCD_WIN_HALF - 0.5) - (f-128)/256)), sc < 2561, f < 256, t < 32.
 __global__ void k_cdf_table(uint32_t *__restrict__ tab, const float *__restrict__ scale) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)CCD_N_SCALE * 256 * CCD_WIN;
@@ -76,7 +76,7 @@ __global__ void k_cdf_table(uint32_t *__restrict__ tab, const float *__restrict_
     int f = (int)((idx >> 5) & 255);
     int sc = (int)(idx >> 13);
     double b = (double)scale[sc];
-    double d = ((double)t - 15.5) - (double)(f - 128) * (1.0 / 256.0);
+    double d = ((double)t - ((double)CCD_WIN_HALF + 0.5)) - (double)(f - 128) * (1.0 / 256.0);
     tab[idx] = laplace_nonleaky(d, b);
 }
 
@@ -167,7 +167,9 @@ struct SmemLayout {
     unsigned char *arm;    // ARM blob
     unsigned char *ifce;   // IFCE blob of the current grid
     uint32_t meta;         // shared address: uint4 [ring]
-    uint32_t win;          // shared address: u32 [ring][32]
+    uint32_t win;          // shared address: u32 [ring][32]: left(s_lo + t), t = 0..31 (mode at t = 15)
+    uint32_t res;          // shared address: u32 [ring]: decoded result of each symbol (coder -> helper)
+    uint32_t bc;           // shared address: 16 B broadcast line of the coder warp (new D, R)
     uint32_t rows;         // shared address: int8 [rows][64]
 };
 
@@ -187,10 +189,14 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int r
     p += align16((size_t)arm_bytes);
     L.ifce = base + p;
     p += align16((size_t)ifce_bytes);
+    L.bc = base_a + (uint32_t)p;
+    p += 16;
     L.meta = base_a + (uint32_t)p;
     p += (size_t)ring * 16;
     L.win = base_a + (uint32_t)p;
     p += (size_t)ring * CCD_WIN * 4;
+    L.res = base_a + (uint32_t)p;
+    p += (size_t)ring * 4;
     L.rows = base_a + (uint32_t)p;
     (void)rows;
     return L;
@@ -226,9 +232,31 @@ struct QuadArm {
         }
     }
 
+    // IFCE inputs of the pixel (y, x): the already decoded coarser grids at (y>>1 >> sh, x>>1 >> sh)
+    // (component/coolchic.py:95-100, core/upsampling.py:575-593).  All loads are issued back to back,
+    // BEFORE the producer waits for its dependencies: their L2 latency is hidden by that wait.
+    static __device__ __forceinline__ void ifce_prefetch(const EntGrid *g, const int8_t *lat, int y, int x, int m,
+                                                         int (&ifv)[CCD_IFCE_FAST_MAX]) {
+#pragma unroll
+        for (int c = 0; c < CCD_IFCE_FAST_MAX; c++) ifv[c] = 0;
+        if constexpr (CF > 0) {
+            const int n_in = g->ifce_in;
+            if (n_in > 0 && (m + 1) * OPM > NCTX) {
+                const int yy = y >> 1, xx = x >> 1;
+#pragma unroll
+                for (int c = 0; c < CCD_IFCE_FAST_MAX; c++) {
+                    if (c < n_in) {
+                        const int sh = g->ch_sh[c];
+                        if (sh >= 0) ifv[c] = lat[g->ch_off[c] + (long long)(yy >> sh) * g->ch_w[c] + (xx >> sh)];
+                    }
+                }
+            }
+        }
+    }
+
     // returns (mu, log-scale) in 1/256 units, identical on the 4 lanes of the quad
     static __device__ __forceinline__ void run(const EntGrid *g, const unsigned char *arm_blob,
-                                               const unsigned char *ifce_blob, const int8_t *lat,
+                                               const unsigned char *ifce_blob, const int (&ifv)[CCD_IFCE_FAST_MAX],
                                                uint32_t rows, uint32_t row_mask, int n_hidden, int y, int x,
                                                int m, long long &o0, long long &o1) {
         const int w = g->w;
@@ -245,7 +273,7 @@ struct QuadArm {
             }
             x0[o] = v;
         }
-        // ---- ... and IFCE features (component/coolchic.py:105-146), evaluated at (y>>1, x>>1)
+        // ---- ... and IFCE features (component/coolchic.py:105-146) from the prefetched inputs
         if constexpr (CF > 0) {
             const int n_in = g->ifce_in;
             if (n_in > 0 && (m + 1) * OPM > NCTX) {
@@ -258,16 +286,15 @@ struct QuadArm {
                     const int f = m * OPM + o - NCTX;
                     acc[o] = (f >= 0 && f < CF) ? B[f] : 0;
                 }
-                const int yy = y >> 1, xx = x >> 1;
-                for (int c = 0; c < n_in; c++) {
-                    const int sh = g->ch_sh[c];
-                    int v = 0;
-                    if (sh >= 0) v = lat[g->ch_off[c] + (long long)(yy >> sh) * g->ch_w[c] + (xx >> sh)];
-                    const int xi = v << 16;
 #pragma unroll
-                    for (int o = 0; o < OPM; o++) {
-                        const int f = m * OPM + o - NCTX;
-                        if (f >= 0 && f < CF) acc[o] += (long long)W[c * CFP + f] * xi;
+                for (int c = 0; c < CCD_IFCE_FAST_MAX; c++) {
+                    if (c < n_in) {
+                        const int xi = ifv[c] << 16;
+#pragma unroll
+                        for (int o = 0; o < OPM; o++) {
+                            const int f = m * OPM + o - NCTX;
+                            if (f >= 0 && f < CF) acc[o] += (long long)W[c * CFP + f] * xi;
+                        }
                     }
                 }
 #pragma unroll
@@ -392,18 +419,12 @@ struct GenericArm {
     }
 };
 
-// window chunk c (4 consecutive cumulatives) of a symbol: table entries + leak term + clamps
-__device__ __forceinline__ uint4 fix_window_chunk(uint4 v, int s_first) {
-    uint32_t e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int s = s_first + q;
-        uint32_t l = e[q] + (uint32_t)(s - kSymMin);
-        l = (s <= kSymMin) ? 0u : l;
-        l = (s > kSymMax) ? (1u << 24) : l;
-        e[q] = l;
-    }
-    return make_uint4(e[0], e[1], e[2], e[3]);
+// cumulative of symbol s from its table entry: leak term + clamps
+__device__ __forceinline__ uint32_t fix_left(uint32_t nl, int s) {
+    uint32_t l = nl + (uint32_t)(s - kSymMin);
+    l = (s <= kSymMin) ? 0u : l;
+    l = (s > kSymMax) ? (1u << 24) : l;
+    return l;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -432,12 +453,17 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
     else need = ord_prev;                                            // first pixel of a row
     const uint32_t need_ring = ord + 1u - (uint32_t)S.ring;          // slot reuse: ord - ring consumed
     if ((int32_t)(need_ring - need) > 0) need = need_ring;
+    int ifv[CCD_IFCE_FAST_MAX];
+    if constexpr (FAST) QuadArm<NCTX, CF>::ifce_prefetch(g, S.latents, valid ? y : y0, valid ? x : x0, member, ifv);
     // needs grow with the lane: one warp-wide wait on the maximum
     int32_t rel = valid ? (int32_t)(need - ord_diag) : INT32_MIN;
     rel = __reduce_max_sync(0xffffffffu, rel);
     need = ord_diag + (uint32_t)rel;
     PROF_T(t0);
     while ((int32_t)(lds_u32(sm.ctrl) - need) < 0) {
+#ifdef CCD_SPIN_SLEEP
+        __nanosleep(CCD_SPIN_SLEEP);
+#endif
     }
     PROF_ADD(pc.wait, t0);
     PROF_T(t1);
@@ -445,7 +471,7 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
     if constexpr (FAST) {
         // all 32 lanes take part (quad shuffles); out-of-range symbols compute on clamped coordinates
         const int yc = valid ? y : y0, xc = valid ? x : x0;
-        QuadArm<NCTX, CF>::run(g, sm.arm, sm.ifce, S.latents, sm.rows, row_mask, S.n_hidden, yc, xc, member, o0, o1);
+        QuadArm<NCTX, CF>::run(g, sm.arm, sm.ifce, ifv, sm.rows, row_mask, S.n_hidden, yc, xc, member, o0, o1);
     } else {
         if (valid) {
             const int n_ctx = S.n_ctx, cf = S.cf;
@@ -477,9 +503,13 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
     const uint32_t wdst = sm.win + slot * (CCD_WIN * 4);
     if constexpr (FAST) {
         if (valid) {
+            // member m owns entries [8m, 8m+8)
             const uint4 va = __ldg(row + 2 * member), vb = __ldg(row + 2 * member + 1);
-            sts_v4(wdst + 32u * member, fix_window_chunk(va, s_lo + 8 * member));
-            sts_v4(wdst + 32u * member + 16u, fix_window_chunk(vb, s_lo + 8 * member + 4));
+            const int s0 = s_lo + 8 * member;
+            sts_v4(wdst + 32u * member, make_uint4(fix_left(va.x, s0), fix_left(va.y, s0 + 1), fix_left(va.z, s0 + 2),
+                                                   fix_left(va.w, s0 + 3)));
+            sts_v4(wdst + 32u * member + 16u, make_uint4(fix_left(vb.x, s0 + 4), fix_left(vb.y, s0 + 5),
+                                                         fix_left(vb.z, s0 + 6), fix_left(vb.w, s0 + 7)));
         }
         __threadfence_block();
         __syncwarp();
@@ -489,7 +519,9 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
 #pragma unroll
             for (int c = 0; c < 8; c++) v[c] = __ldg(row + c);
 #pragma unroll
-            for (int c = 0; c < 8; c++) sts_v4(wdst + 16u * c, fix_window_chunk(v[c], s_lo + 4 * c));
+            for (int c = 0; c < 8; c++)
+                sts_v4(wdst + 16u * c, make_uint4(fix_left(v[c].x, s_lo + 4 * c), fix_left(v[c].y, s_lo + 4 * c + 1),
+                                                  fix_left(v[c].z, s_lo + 4 * c + 2), fix_left(v[c].w, s_lo + 4 * c + 3)));
             __threadfence_block();
         }
     }
@@ -606,49 +638,19 @@ __device__ __noinline__ void encoder_emit(const SLoc &S, Coder &c, uint32_t L0, 
     }
 }
 
-struct SymIn {
-    uint4 m;      // x: output offset, y: row-ring index | (s_lo+128) << 16, z: mu_idx | sc_idx << 16, w: ordinal + 1
-    uint32_t L0;  // this lane's left cumulative (candidate symbol s_lo + lane)
-    uint32_t L1;  // the next lane's (lane 31: its own -> empty interval)
-};
-
-// Inputs of symbol j.  The window load is made ADDRESS-DEPENDENT on the tag load, so the
-// hardware cannot service it first: a valid tag implies a valid window (the producer writes
-// window -> fence -> tag).
-__device__ __forceinline__ void load_sym_meta(const SmemLayout &sm, uint32_t ring_mask, uint32_t j, SymIn &s) {
-    s.m = lds_v4(sm.meta + (j & ring_mask) * 16u);
-}
-__device__ __forceinline__ void load_sym_win(const SmemLayout &sm, uint32_t ring_mask, uint32_t j, uint32_t lane4,
-                                             SymIn &s) {
-    uint32_t a = sm.win + (j & ring_mask) * (CCD_WIN * 4) + lane4;
-    asm volatile("{\n .reg .b32 t;\n and.b32 t, %1, 0;\n add.u32 %0, %0, t;\n}\n" : "+r"(a) : "r"(s.m.w));
-    s.L0 = lds_u32(a);
-}
-__device__ __forceinline__ void load_sym(const SmemLayout &sm, uint32_t ring_mask, uint32_t j, uint32_t lane4,
-                                         SymIn &s) {
-    load_sym_meta(sm, ring_mask, j, s);
-    load_sym_win(sm, ring_mask, j, lane4, s);
-}
-
-// Publish the decoded symbol: row ring, global latent array, progress counter.  One
-// predicated store per instruction, no divergent branch on the coder's in-order stream.
-// The progress counter is written last (same lane as the row byte: program order).
-__device__ __forceinline__ void publish_symbol(int lane, uint32_t row_addr, int8_t *gptr, uint32_t ctrl_addr,
-                                               int sym, uint32_t progress) {
-    asm volatile(
-        "{\n"
-        " .reg .pred p0, p1;\n"
-        " setp.eq.s32 p0, %0, 0;\n"
-        " setp.eq.s32 p1, %0, 1;\n"
-        " @p1 st.global.u8 [%3], %2;\n"
-        " @p0 st.volatile.shared.u8 [%1], %2;\n"
-        " @p0 st.volatile.shared.u32 [%4], %5;\n"
-        "}\n" ::"r"(lane),
-        "r"(row_addr), "r"(sym), "l"(gptr), "r"(ctrl_addr), "r"(progress)
-        : "memory");
-}
-
-// ---- decode.  Uniform state D, R in registers.
+// =======================================================================================
+// Range DEcoder = two warps.
+//   coder  (warp 15): only the (D, R) recursion, executed identically by all its lanes: a
+//          scalar most-probable-first search over the 8 cumulatives around the mode (two
+//          broadcast LDS.128, prefetched), pure 64-bit integer ALU on the serial chain.
+//          (Measured on B200: every vote / shuffle / shared-memory round trip costs 27-35
+//          cycles, a dependent ALU op ~5: lane-parallel candidate evaluation loses.)
+//   helper (warp 14): everything that is not on that recursion, 32 symbols at a time:
+//          finds how far the producers have got (contiguous valid tags -> `ready`), turns the
+//          coder's per-symbol results into symbols, writes the row ring / latent array and
+//          advances `progress` for the producers.
+// ctrl words: [0] progress (symbols published), [1] ready (symbols whose window is in the ring)
+// =======================================================================================
 struct DecState {
     uint64_t D, R;        // D = point - lower (mod 2^64), R = range   
     int64_t wpos;         // index of the next unread word
@@ -667,135 +669,221 @@ __device__ __noinline__ void dec_advance_word(const SLoc &S, DecState &c, int la
     c.wnext = __shfl_sync(0xffffffffu, c.wcur, (int)(c.wpos & 31));
 }
 
-// Serial chain of one symbol, `cur` validated.  Every lane owns one
-// candidate symbol [L0, L1); the lane whose scaled interval contains D wins (no division):
-// products -> compare -> vote -> bfind -> 4 shuffles.  Everything else is kept off that chain.
-__device__ __forceinline__ void decode_chain(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
-                                             int lane, uint32_t j, const SymIn &cur, uint64_t &D, uint64_t &R,
-                                             uint32_t &wnext, DecState &c, ProfCounters &pc) {
-    const uint64_t scale = R >> 24;
-    const uint64_t P0 = scale * cur.L0, P1 = scale * cur.L1;
-    const uint64_t Dn = D - P0, Rn = P1 - P0;  // candidate new state of this lane
-    const uint32_t ballot = __ballot_sync(0xffffffffu, (P0 <= D) && (D < P1));
-    uint32_t usrc;
-    asm("bfind.u32 %0, %1;" : "=r"(usrc) : "r"(ballot));  // the single set bit (0xffffffff if none)
-    int src = (int)usrc;
-    uint64_t D2 = shfl_u64(Dn, src), R2 = shfl_u64(Rn, src);
-    int sym = (int)(cur.m.y >> 16) - 128 + src;
-    if (ballot == 0u) {
-        // no lane won: symbol outside the 31-symbol window, or corrupt stream
-        c.slow++;
-        uint64_t q = D / scale;
-        if (q >= (1ull << 24)) {
-            c.err = CCD_ERR_DESYNC;
-            q = (1ull << 24) - 1;
+// result word of symbol j: [31] value is the symbol itself (else the window index t), [30:8] tag, [7:0] value
+__device__ __forceinline__ uint32_t res_word(uint32_t j, uint32_t value, bool is_symbol) {
+    return ((uint32_t)is_symbol << 31) | (((j + 1u) & 0x7fffffu) << 8) | (value & 0xffu);
+}
+
+struct FarOut {
+    uint64_t lo, hi;
+    uint32_t rw;
+};
+
+// Symbol is not the mode: neighbours of the mode first, then the rest of the 32-entry window,
+// then the exact f64 model (warp-cooperative).  Out of line: keeps the hot loop small.
+__device__ __noinline__ FarOut coder_far(const SmemLayout &sm, const float *__restrict__ scale_tab, uint32_t ring_mask,
+                                         int lane, uint32_t j, uint64_t scale, uint64_t D, uint32_t *slow, int *err) {
+    FarOut o;
+    const uint32_t wrow = sm.win + (j & ring_mask) * (CCD_WIN * 4);
+    // the mode sits at t = M: scan down while D < P[t], or up while D >= P[t+1]
+    constexpr int M = CCD_WIN_HALF;
+    const uint64_t PM = scale * lds_u32(wrow + 4u * M);
+    if (D < PM) {
+        uint64_t hi = PM;
+        for (int t = M - 1; t >= 0; t--) {
+            const uint64_t lo = scale * lds_u32(wrow + 4u * (uint32_t)t);
+            if (lo <= D) {
+                o.lo = lo; o.hi = hi; o.rw = res_word(j, (uint32_t)t, false);
+                return o;
+            }
+            hi = lo;
         }
-        const uint4 r = slow_search((uint32_t)q, (int)(cur.m.z & 0xffffu), (int)(cur.m.z >> 16), scale_tab, lane);
-        src = (int)r.z;
-        sym = (int)r.w;
-        const uint64_t Q0 = scale * r.x, Q1 = scale * r.y;
-        D2 = shfl_u64(D - Q0, src);
-        R2 = shfl_u64(Q1 - Q0, src);
+    } else {
+        uint64_t lo = scale * lds_u32(wrow + 4u * (M + 1));  // P[M+1] <= D here
+        for (int t = M + 1; t < 31; t++) {
+            const uint64_t hi = scale * lds_u32(wrow + 4u * (uint32_t)(t + 1));
+            if (D < hi) {
+                o.lo = lo; o.hi = hi; o.rw = res_word(j, (uint32_t)t, false);
+                return o;
+            }
+            lo = hi;
+        }
     }
-    D = D2;
-    R = R2;
+    // outside the window, or corrupt stream
+    (*slow)++;
+    uint64_t q = D / scale;
+    if (q >= (1ull << 24)) {
+        *err = CCD_ERR_DESYNC;
+        q = (1ull << 24) - 1;
+    }
+    const uint4 m = lds_v4(sm.meta + (j & ring_mask) * 16u);
+    const uint4 r = slow_search((uint32_t)q, (int)(m.z & 0xffffu), (int)(m.z >> 16), scale_tab, lane);
+    o.lo = scale * (uint64_t)__shfl_sync(0xffffffffu, r.x, (int)r.z);
+    o.hi = scale * (uint64_t)__shfl_sync(0xffffffffu, r.y, (int)r.z);
+    o.rw = res_word(j, r.w, true);
+    return o;
+}
+
+// One symbol of the recursion, executed IDENTICALLY by every lane of the coder warp: no vote,
+// no shuffle, no shared-memory round trip on the serial chain -- only 64-bit integer ALU ops.
+// LM = (left(mode), left(mode + 1)): the most probable symbol is tested speculatively.
+__device__ __forceinline__ void coder_step(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                           uint32_t ring_mask, int lane, uint32_t j, uint2 LM, uint64_t &D,
+                                           uint64_t &R, uint32_t &wnext, DecState &c) {
+    const uint64_t scale = R >> 24;
+    uint64_t lo = scale * LM.x, hi = scale * LM.y;
+    uint32_t rw = res_word(j, (uint32_t)CCD_WIN_HALF, false);
+    if (!((lo <= D) && (D < hi))) {
+        const FarOut f = coder_far(sm, scale_tab, ring_mask, lane, j, scale, D, &c.slow, &c.err);
+        lo = f.lo;
+        hi = f.hi;
+        rw = f.rw;
+    }
+    D -= lo;
+    R = hi - lo;
+    asm volatile(
+        "{\n .reg .pred p;\n setp.eq.s32 p, %0, 0;\n @p st.volatile.shared.u32 [%1], %2;\n}\n" ::"r"(lane),
+        "r"(sm.res + (j & ring_mask) * 4u), "r"(rw)
+        : "memory");
     if ((R >> 32) == 0) {  // at most one renormalisation per symbol
         R <<= 32;
         D = (D << 32) | wnext;
         dec_advance_word(S, c, lane);
         wnext = c.wnext;
     }
-    publish_symbol(lane, sm.rows + (cur.m.y & 0xffffu), S.latents + cur.m.x, sm.ctrl, sym, j + 1u);
-    (void)pc;
 }
 
-// One pipelined step.  The warp issues in order, so the statement order IS the schedule:
-//   L(j+2): request the inputs of symbol j+2 (LDS);
-//   V(j+1): validate symbol j+1 (loaded one step ago: no stall in the common case) and
-//           derive its upper bounds with one SHFL.DOWN;
-//   C(j)  : the serial chain of symbol j (products -> compare -> masked OR-reductions).
-__device__ __forceinline__ void decode_step3(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
-                                             uint32_t ring_mask, int lane, uint32_t lane4, uint32_t j, SymIn &s0,
-                                             SymIn &s1, SymIn &s2, uint64_t &D, uint64_t &R, uint32_t &wnext,
-                                             DecState &c, ProfCounters &pc) {
-    load_sym(sm, ring_mask, j + 2u, lane4, s2);
-    // Readiness must be a warp-wide agreement: lanes may have loaded the tag at slightly
-    // different times, and the shuffle below needs every lane on the same side of the branch.
-    // Never BLOCK on symbol j+1 before symbol j is published: its producer may be waiting
-    // for symbol j (short diagonals, raster grids).
-    const bool ready = __all_sync(0xffffffffu, s1.m.w == j + 2u);
-    if (ready) s1.L1 = __shfl_down_sync(0xffffffffu, s1.L0, 1);
-    decode_chain(S, sm, scale_tab, lane, j, s0, D, R, wnext, c, pc);
-    if (!ready) {
-        PROF_T(t0);
-        do {
-            load_sym(sm, ring_mask, j + 1u, lane4, s1);
-        } while (!__all_sync(0xffffffffu, s1.m.w == j + 2u));
-        PROF_ADD(pc.wait, t0);
-        s1.L1 = __shfl_down_sync(0xffffffffu, s1.L0, 1);
-    }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
 }
 
-__device__ __forceinline__ void decode_step1(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
-                                             uint32_t ring_mask, int lane, uint32_t lane4, uint32_t j, uint64_t &D,
-                                             uint64_t &R, uint32_t &wnext, DecState &c, ProfCounters &pc) {
-    SymIn s0;
-    PROF_T(t0);
-    do {
-        load_sym(sm, ring_mask, j, lane4, s0);
-    } while (!__all_sync(0xffffffffu, s0.m.w == j + 1u));
-    PROF_ADD(pc.wait, t0);
-    s0.L1 = __shfl_down_sync(0xffffffffu, s0.L0, 1);
-    decode_chain(S, sm, scale_tab, lane, j, s0, D, R, wnext, c, pc);
-}
-
-__device__ __forceinline__ void decode_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
-                                            int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
-                                            ProfCounters &pc) {
+__device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                           int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
+                                           ProfCounters &pc) {
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
-    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const uint32_t ready_a = sm.ctrl + 4u;
     uint64_t D = c.D, R = c.R;
     uint32_t wnext = c.wnext;
     uint32_t j = ord_begin;
-    if (ord_end - ord_begin > 8u) {
-        SymIn a, b, d;
-        do {
-            load_sym(sm, ring_mask, j, lane4, a);
-        } while (!__all_sync(0xffffffffu, a.m.w == j + 1u));
-        a.L1 = __shfl_down_sync(0xffffffffu, a.L0, 1);
-        load_sym(sm, ring_mask, j + 1u, lane4, b);
-        // three-buffer rotation, unrolled: no register moves between steps.  Steps touch
-        // symbols up to j+2, so stop 2 before the end of the grid.
-        const uint32_t stop = ord_end - 2u;
-        while (j + 3u <= stop) {
-            decode_step3(S, sm, scale_tab, ring_mask, lane, lane4, j, a, b, d, D, R, wnext, c, pc);
-            decode_step3(S, sm, scale_tab, ring_mask, lane, lane4, j + 1u, b, d, a, D, R, wnext, c, pc);
-            decode_step3(S, sm, scale_tab, ring_mask, lane, lane4, j + 2u, d, a, b, D, R, wnext, c, pc);
+    uint32_t limit = ord_begin;  // symbols < limit have their window in the ring
+    auto refresh = [&]() {
+        const uint32_t r = lds_u32(ready_a);
+        limit = ((int32_t)(r - ord_end) > 0) ? ord_end : r;
+    };
+    // (left(mode), left(mode+1)) = window entries 15, 16 of symbol jj: one 8-byte aligned LDS.64
+    auto mode_of = [&](uint32_t jj) { return lds_v2(sm.win + (jj & ring_mask) * (CCD_WIN * 4) + 4u * CCD_WIN_HALF); };
+    while (j != ord_end) {
+        if ((int32_t)(limit - j) <= 0) {
+            PROF_T(t0);
+            do {
+                refresh();
+            } while ((int32_t)(limit - j) <= 0);
+            PROF_ADD(pc.wait, t0);
+        }
+        if ((int32_t)(limit - j) >= 6) {
+            // steady state, three symbols per round trip through the loop: the cumulatives of
+            // symbols j+3..j+5 are requested while j..j+2 are decoded (no register rotation)
+            uint2 a0 = mode_of(j), a1 = mode_of(j + 1u), a2 = mode_of(j + 2u);
+            while (true) {
+                if ((int32_t)(limit - j) < 6) {
+                    refresh();
+                    if ((int32_t)(limit - j) < 6) break;
+                }
+                const uint2 b0 = mode_of(j + 3u), b1 = mode_of(j + 4u), b2 = mode_of(j + 5u);
+                coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c);
+                coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c);
+                coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c);
+                j += 3u;
+                a0 = b0;
+                a1 = b1;
+                a2 = b2;
+            }
+            // a0..a2 are valid (limit - j >= 3 here)
+            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c);
             j += 3u;
+        } else {
+            const uint2 a0 = mode_of(j);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c);
+            j++;
         }
     }
-    for (; j < ord_end; j++) decode_step1(S, sm, scale_tab, ring_mask, lane, lane4, j, D, R, wnext, c, pc);
     c.D = D;
     c.R = R;
     c.wnext = wnext;
 }
 
+// Helper warp: readiness scan + publication, 32 symbols per round (lane = symbol).
+__device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm, int lane, uint32_t ord_begin,
+                                            uint32_t ord_end, ProfCounters &pc) {
+    const uint32_t ring_mask = (uint32_t)S.ring - 1u;
+    uint32_t r = ord_begin, p = ord_begin;
+    while (p != ord_end) {
+#ifdef CCD_PROFILE
+        pc.seg[0]++;  // rounds
+#endif
+        if (r != ord_end) {
+            const uint32_t jj = r + (uint32_t)lane;
+            bool ok = false;
+            if ((int32_t)(ord_end - jj) > 0) ok = lds_u32(sm.meta + (jj & ring_mask) * 16u + 12u) == jj + 1u;
+            const uint32_t b = __ballot_sync(0xffffffffu, ok);
+            const uint32_t cnt = (b == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~b) - 1);
+            if (cnt) {
+                r += cnt;
+                if (lane == 0) sts_u32(sm.ctrl + 4u, r);
+            }
+#ifdef CCD_PROFILE
+            pc.seg[1] += cnt;
+            if (cnt == 32u) pc.seg[2]++;
+            pc.seg[3] += (int32_t)(r - p);  // ready - published
+#endif
+        }
+        {
+            const uint32_t jj = p + (uint32_t)lane;
+            bool ok = false;
+            uint32_t w = 0;
+            if ((int32_t)(r - jj) > 0) {
+                w = lds_u32(sm.res + (jj & ring_mask) * 4u);
+                ok = ((w >> 8) & 0x7fffffu) == ((jj + 1u) & 0x7fffffu);
+            }
+            const uint32_t b = __ballot_sync(0xffffffffu, ok);
+            const uint32_t cnt = (b == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~b) - 1);
+            if ((uint32_t)lane < cnt) {
+                const uint4 m = lds_v4(sm.meta + (jj & ring_mask) * 16u);
+                const int v = (int)(w & 0xffu);
+                const int sym = (w >> 31) ? (int)(int8_t)v : ((int)(m.y >> 16) - 128 + v);
+                sts_u8(sm.rows + (m.y & 0xffffu), sym);
+                S.latents[m.x] = (int8_t)sym;
+            }
+            __syncwarp();
+            if (cnt) {
+                p += cnt;
+                if (lane == 0) sts_u32(sm.ctrl, p);
+            }
+        }
+    }
+}
+
 // ---- encode (MODE 1: the latents given in S.latents; MODE 2: draw them from the model).
-// Not performance critical: used to fabricate synthetic streams.
+// Not performance critical: used to fabricate synthetic streams.  Runs in the coder warp and
+// publishes by itself (the helper warp idles).
 template <int MODE>
 __device__ __noinline__ void encode_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
                                          int lane, uint32_t ord_begin, uint32_t ord_end, Coder &c) {
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
-    const uint32_t lane4 = (uint32_t)lane * 4u;
     for (uint32_t j = ord_begin; j != ord_end; j++) {
-        SymIn cur;
+        const uint32_t slot = j & ring_mask;
+        uint4 m;
         do {
-            load_sym(sm, ring_mask, j, lane4, cur);
-        } while (!__all_sync(0xffffffffu, cur.m.w == j + 1u));
-        const uint32_t L0 = cur.L0;
-        const uint32_t L1 = __shfl_down_sync(0xffffffffu, L0, 1);
-        const int mu_idx = (int)(cur.m.z & 0xffffu), sc_idx = (int)(cur.m.z >> 16);
-        const int s_lo = (int)(cur.m.y >> 16) - 128;
+            m = lds_v4(sm.meta + slot * 16u);
+        } while (!__all_sync(0xffffffffu, m.w == j + 1u));
+        const uint32_t L0 = lds_u32(sm.win + slot * (CCD_WIN * 4) + (uint32_t)lane * 4u);
+        const uint32_t L1 = __shfl_down_sync(0xffffffffu, L0, 1);  // lane 31 keeps L0: empty interval
+        const int mu_idx = (int)(m.z & 0xffffu), sc_idx = (int)(m.z >> 16);
+        const int s_lo = (int)(m.y >> 16) - 128;
         uint32_t l0, l1;
         int src = -1, sym;
         if constexpr (MODE == 2) {
@@ -815,7 +903,7 @@ __device__ __noinline__ void encode_grid(const SLoc &S, const SmemLayout &sm, co
                 l1 = __shfl_sync(0xffffffffu, r.y, src);
             }
         } else {
-            sym = S.latents[cur.m.x];
+            sym = S.latents[m.x];
             if (sym >= s_lo && sym < s_lo + 31) {
                 src = sym - s_lo;
                 l0 = __shfl_sync(0xffffffffu, L0, src);
@@ -829,10 +917,11 @@ __device__ __noinline__ void encode_grid(const SLoc &S, const SmemLayout &sm, co
         }
         encoder_emit(S, c, l0, l1, lane);
         if (lane == 0) {
-            sts_u8(sm.rows + (cur.m.y & 0xffffu), sym);
-            S.latents[cur.m.x] = (int8_t)sym;
+            sts_u8(sm.rows + (m.y & 0xffffu), sym);
+            S.latents[m.x] = (int8_t)sym;
             sts_u32(sm.ctrl, j + 1u);
         }
+        __syncwarp();
     }
 }
 
@@ -848,16 +937,18 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EntStream &G = streams[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // role assignment: the last warp is the range coder; producer warps are those enabled in
-    // prod_mask (by default the coder keeps its scheduler partition for itself)
-    const uint32_t prod_mask = G.prod_mask & ((1u << (CCD_ENT_WARPS - 1)) - 1u);
+    // role assignment: warp 15 = range coder (recursion), warp 14 = its helper; producer warps are
+    // those enabled in prod_mask (by default the coder keeps its scheduler partition for itself)
+    const uint32_t prod_mask = G.prod_mask & ((1u << (CCD_ENT_WARPS - 2)) - 1u);
     const bool is_coder = (warp == CCD_ENT_WARPS - 1);
-    const bool is_prod = !is_coder && ((prod_mask >> warp) & 1u);
-    if (!is_coder && !is_prod) return;
+    const bool is_helper = (warp == CCD_ENT_WARPS - 2);
+    const bool is_prod = !is_coder && !is_helper && ((prod_mask >> warp) & 1u);
+    if (!is_coder && !is_helper && !is_prod) return;
     const int n_prod = __popc(prod_mask);
     const int prank = __popc(prod_mask & ((1u << warp) - 1u));
-    const int n_active = (n_prod + 1) * 32;
-    const int atid = is_coder ? n_prod * 32 + lane : prank * 32 + lane;  // dense index among active threads
+    const int n_active = (n_prod + 2) * 32;
+    // dense index among active threads
+    const int atid = is_coder ? (n_prod + 1) * 32 + lane : (is_helper ? n_prod * 32 + lane : prank * 32 + lane);
 
     SmemLayout sm = carve(smem_raw, G.ring, G.rows, G.arm_blob_bytes, G.ifce_blob_max);
     SLoc S;
@@ -877,7 +968,10 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
 
     // one-time: control words, meta tags, ARM parameters
     if (atid < 16) sts_u32(sm.ctrl + 4u * atid, 0u);
-    for (int i = atid; i < S.ring; i += n_active) sts_v4(sm.meta + 16u * i, make_uint4(0, 0, 0, 0));
+    for (int i = atid; i < S.ring; i += n_active) {
+        sts_v4(sm.meta + 16u * i, make_uint4(0, 0, 0, 0));
+        sts_u32(sm.res + 4u * i, 0u);
+    }
     for (int i = atid * 4; i < G.arm_blob_bytes; i += n_active * 4)
         *reinterpret_cast<uint32_t *>(sm.arm + i) = *reinterpret_cast<const uint32_t *>(G.blob + i);
 
@@ -921,9 +1015,11 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
         const uint32_t n_sym = (uint32_t)sm.grid->h * (uint32_t)sm.grid->w;
         PROF_T(tg);
         if (is_coder) {
-            if (S.mode == 0) decode_grid(S, sm, scale_tab, lane, ord, ord + n_sym, ds, pc);
+            if (S.mode == 0) coder_grid(S, sm, scale_tab, lane, ord, ord + n_sym, ds, pc);
             else if (S.mode == 1) encode_grid<1>(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
             else encode_grid<2>(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
+        } else if (is_helper) {
+            if (S.mode == 0) helper_grid(S, sm, lane, ord, ord + n_sym, pc);
         } else {
             producer_grid<NCTX, CF, FAST>(S, sm, cdf, prank, n_prod, lane, ord, chunk_ctr, pc);
         }
@@ -932,15 +1028,21 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     }
 #ifdef CCD_PROFILE
     // [4] coder wait, [5] coder total, [6] producers wait, [7] arm, [8] window, [9] total (kilo-cycles, lane 0 of each warp)
-    if (lane == 0) {
+    if (lane == 0 && is_helper) {
+        G.status[6] = (int)pc.seg[0];
+        G.status[7] = (int)pc.seg[1];
+        G.status[8] = (int)pc.seg[2];
+        G.status[9] = (int)(pc.seg[3] >> 4);
+        G.status[15] = (int)(pc.total >> 10);
+    } else if (lane == 0) {
         if (is_coder) {
             atomicAdd(&G.status[4], (int)(pc.wait >> 10));
             atomicAdd(&G.status[5], (int)(pc.total >> 10));
-        } else {
-            atomicAdd(&G.status[6], (int)(pc.wait >> 10));
-            atomicAdd(&G.status[7], (int)(pc.arm >> 10));
-            atomicAdd(&G.status[8], (int)(pc.win >> 10));
-            atomicAdd(&G.status[9], (int)(pc.total >> 10));
+            G.status[10] = (int)pc.seg[0];
+            G.status[11] = (int)pc.seg[1];
+            G.status[12] = (int)pc.seg[2];
+            G.status[13] = (int)(pc.seg[3] >> 4);
+            G.status[14] = (int)(pc.seg[4] >> 4);
         }
     }
 #endif
@@ -990,7 +1092,7 @@ unsigned long long g_ccd_launches = 0;
 
 size_t ccd_entropy_smem_bytes(int ring, int rows, int arm_blob_bytes, int ifce_blob_max) {
     size_t p = 64 + align16(sizeof(EntGrid)) + align16((size_t)arm_blob_bytes) + align16((size_t)ifce_blob_max);
-    p += (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)rows * CCD_ROW_COLS;
+    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)ring * 4 + (size_t)rows * CCD_ROW_COLS;
     return p;
 }
 

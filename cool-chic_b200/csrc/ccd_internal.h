@@ -9,12 +9,14 @@
 // --------------------------------------------------------------------------------------
 // Entropy stage (ccd_entropy.cu): one persistent CTA per Cool-chic stream.
 // --------------------------------------------------------------------------------------
-#define CCD_ENT_THREADS 512          // 15 producer warps + 1 range-coder warp
+#define CCD_ENT_THREADS 512          // <= 14 producer warps + helper warp + range-coder warp
 #define CCD_ENT_WARPS (CCD_ENT_THREADS / 32)
-#define CCD_ENT_PRODUCERS (CCD_ENT_WARPS - 1)
+#define CCD_ENT_PRODUCERS (CCD_ENT_WARPS - 2)
 #define CCD_WIN 32                   // cumulative-window entries per symbol (31 decodable symbols)
-#define CCD_WIN_HALF 15              // window covers mu_int-15 .. mu_int+15
+#define CCD_WIN_HALF 14              // window = symbols mu_int-14 .. mu_int+16; the mode sits at the EVEN index 14
+                                     // so that (left(mode), left(mode+1)) is one aligned LDS.64
 #define CCD_ROW_COLS 64              // row ring: columns kept per row (power of 2)
+#define CCD_IFCE_FAST_MAX 12         // IFCE inputs handled by the fast (quad) kernel; more -> generic kernel
 #define CCD_MAX_DIM 72               // n_ctx (<=40) + n_ifce_out (<=31)
 #define CCD_N_SCALE 2561
 #define CCD_MASK_STRIDE 10           // wavefront stride = ARM mask size 9 + 1 (latent.py:63,72)
@@ -41,7 +43,7 @@ struct EntStream {
     int32_t ring;          // window ring entries (power of two)
     int32_t rows;          // row ring rows (power of two)
     int32_t mode;          // 0 decode, 1 encode given latents, 2 sample + encode
-    uint32_t prod_mask;    // which of warps 0..14 produce (warp 15 is the range coder)
+    uint32_t prod_mask;    // which of warps 0..13 produce (14 = coder helper, 15 = range coder)
     const uint32_t *words; // compressed words (device)
     int64_t n_words;
     int8_t *latents;       // device, decode order
