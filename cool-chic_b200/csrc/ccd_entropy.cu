@@ -685,12 +685,19 @@ __device__ __noinline__ FarOut coder_far(const SmemLayout &sm, const float *__re
                                          int lane, uint32_t j, uint64_t scale, uint64_t D, uint32_t *slow, int *err) {
     FarOut o;
     const uint32_t wrow = sm.win + (j & ring_mask) * (CCD_WIN * 4);
-    // the mode sits at t = M: scan down while D < P[t], or up while D >= P[t+1]
+    // The mode sits at t = M.  Its neighbours t = M-2 .. M+4 are fetched with two LDS.128 issued
+    // together and tested with ALU ops only; farther symbols walk the window one LDS at a time.
     constexpr int M = CCD_WIN_HALF;
-    const uint64_t PM = scale * lds_u32(wrow + 4u * M);
+    const uint4 A = lds_v4(wrow + 4u * (M - 2));  // left(M-2), left(M-1), left(M), left(M+1)
+    const uint4 B = lds_v4(wrow + 4u * (M + 2));  // left(M+2) .. left(M+5)
+    const uint64_t PM = scale * A.z;
     if (D < PM) {
-        uint64_t hi = PM;
-        for (int t = M - 1; t >= 0; t--) {
+        const uint64_t P1 = scale * A.y;
+        if (P1 <= D) { o.lo = P1; o.hi = PM; o.rw = res_word(j, M - 1, false); return o; }
+        const uint64_t P2 = scale * A.x;
+        if (P2 <= D) { o.lo = P2; o.hi = P1; o.rw = res_word(j, M - 2, false); return o; }
+        uint64_t hi = P2;
+        for (int t = M - 3; t >= 0; t--) {
             const uint64_t lo = scale * lds_u32(wrow + 4u * (uint32_t)t);
             if (lo <= D) {
                 o.lo = lo; o.hi = hi; o.rw = res_word(j, (uint32_t)t, false);
@@ -699,8 +706,17 @@ __device__ __noinline__ FarOut coder_far(const SmemLayout &sm, const float *__re
             hi = lo;
         }
     } else {
-        uint64_t lo = scale * lds_u32(wrow + 4u * (M + 1));  // P[M+1] <= D here
-        for (int t = M + 1; t < 31; t++) {
+        const uint64_t Q1 = scale * A.w;  // P[M+1] <= D here (the mode was rejected)
+        const uint64_t Q2 = scale * B.x;
+        if (D < Q2) { o.lo = Q1; o.hi = Q2; o.rw = res_word(j, M + 1, false); return o; }
+        const uint64_t Q3 = scale * B.y;
+        if (D < Q3) { o.lo = Q2; o.hi = Q3; o.rw = res_word(j, M + 2, false); return o; }
+        const uint64_t Q4 = scale * B.z;
+        if (D < Q4) { o.lo = Q3; o.hi = Q4; o.rw = res_word(j, M + 3, false); return o; }
+        const uint64_t Q5 = scale * B.w;
+        if (D < Q5) { o.lo = Q4; o.hi = Q5; o.rw = res_word(j, M + 4, false); return o; }
+        uint64_t lo = Q5;
+        for (int t = M + 5; t < 31; t++) {
             const uint64_t hi = scale * lds_u32(wrow + 4u * (uint32_t)(t + 1));
             if (D < hi) {
                 o.lo = lo; o.hi = hi; o.rw = res_word(j, (uint32_t)t, false);
