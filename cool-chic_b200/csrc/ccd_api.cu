@@ -1017,9 +1017,21 @@ int ccd_finish_frame(CcdContext *ctx, const float *d_in, int h, int w, int bitde
     return CCD_OK;
 }
 
-int ccd_inter_predict(CcdContext *, const float *, const float *, const float *, const float *, int, int, int,
-                      const int32_t *, int, float *, void *) {
-    return fail(CCD_ERR_UNSUPPORTED, "P/B frame reconstruction is not implemented yet");
+int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_motion, const float *d_ref0,
+                      const float *d_ref1, int h, int w, int is_b, const int32_t *global_flow, int warp_filter_size,
+                      float *d_out, void *cuda_stream) {
+    if (!ctx || !d_residue || !d_motion || !d_ref0 || !d_out || !global_flow || h < 2 || w < 2 || (is_b && !d_ref1))
+        return fail(CCD_ERR_ARG, "bad argument");
+    if (warp_filter_size == 2 || warp_filter_size == 4)
+        return fail(CCD_ERR_UNSUPPORTED, "bilinear / bicubic warps (filter_size 2, 4) are not implemented yet");
+    if (warp_filter_size < 6 || (warp_filter_size & 1)) return fail(CCD_ERR_ARG, "bad warp filter size %d", warp_filter_size);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int32_t gf[4] = {global_flow[0], global_flow[1], is_b ? global_flow[2] : 0, is_b ? global_flow[3] : 0};
+    int rc = ccd_inter_launch(d_residue, d_motion, d_ref0, d_ref1, h, w, is_b, gf, warp_filter_size, d_out,
+                              (cudaStream_t)cuda_stream);
+    if (rc == -1) return fail(CCD_ERR_UNSUPPORTED, "warp filter size %d is not instantiated (6, 8, 10, 12 are)", warp_filter_size);
+    if (rc) return fail(CCD_ERR_CUDA, "inter_predict launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    return CCD_OK;
 }
 
 int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *out_lo, uint32_t *out_hi) {

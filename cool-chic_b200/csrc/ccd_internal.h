@@ -108,3 +108,7 @@ int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st);
 int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st);
 int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, float *a, float *b, float *c,
                cudaStream_t st);
+
+// P/B reconstruction (ccd_inter.cu); returns -1 for an unsupported filter size
+int ccd_inter_launch(const float *d_residue, const float *d_motion, const float *d_ref0, const float *d_ref1, int h,
+                     int w, int is_b, const int32_t *gf, int filter_size, float *d_out, cudaStream_t st);

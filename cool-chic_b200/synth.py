@@ -212,16 +212,23 @@ def make_coolchic_header(template: CoolChicHeader, img_size: Tuple[int, int], la
 
 
 class SeedStream:
-    """The shipped 768x512 sample, decoded once on the device (latents + network integers)."""
+    """The shipped 768x512 sample, decoded once (latents + network integers).
+
+    ``ctx`` is a ``_native.Context`` (device) -- or any object with the same three methods
+    ``decode_nn(desc, bytes)``, ``decode_latents(desc, nn, bytes)``, ``encode_latents(desc, nn, latents=)``
+    (the CPU tests pass an oracle-backed one)."""
 
     def __init__(self, ctx, path: str = SEED_STREAM):
-        from . import _native
-
         with open(path, "rb") as f:
             data = f.read()
         self.video, self.frame, self.header, nn_bytes, lat_bytes = parse_single_image(data)
         self.desc = desc_from_header(self.header)
-        self.nn = _native.decode_nn(self.desc, nn_bytes)
+        if hasattr(ctx, "decode_nn"):
+            self.nn = ctx.decode_nn(self.desc, nn_bytes)
+        else:
+            from . import _native
+
+            self.nn = _native.decode_nn(self.desc, nn_bytes)
         self.latents = ctx.decode_latents(self.desc, self.nn, lat_bytes)
 
 
@@ -255,3 +262,55 @@ def make_image_stream(ctx, seed_stream: SeedStream, height: int, width: int, fra
                      index_references=[], global_flow=[])
     cc, _, _ = make_coolchic(ctx, seed_stream, (height, width), latent_resolution, hyperlatent_resolution, seed)
     return v.to_bytes() + f.to_bytes() + cc
+
+
+# ---- video (I / P / hierarchical B) -------------------------------------------------------------
+def _syn_overrides(width: int, out_ch: int, n_layers: int) -> dict:
+    layers = [f"{width}-1-linear-relu", f"{out_ch}-1-linear-none", f"{out_ch}-3-residual-relu",
+              f"{out_ch}-3-residual-none"][:n_layers]
+    ov = {"n_layer_synthesis": n_layers}
+    for i, lay in enumerate(layers):
+        ov[f"syn_layer_{i}"] = lay
+    return ov
+
+
+def make_video_stream(ctx, seed_stream: SeedStream, height: int, width: int, n_frames: int,
+                      frame_data_type: str = "yuv420", bitdepth: int = 8, warp_filter_size: int = 8,
+                      seed: int = 0) -> bytes:
+    """A GOP: I frame, last frame P, hierarchical B in between (codingstructure.py:267-436).
+    Architectures follow cfg/dec: intra = hop; residue of P/B = mop widths (ARM 10+2, 16-wide
+    synthesis, 4 / 5 output channels); motion = mop (latent_resolution 2-6, ARM 6+2, 16-wide
+    synthesis with 2 / 4 outputs, nearest final upsampling)."""
+    from .utils.codingstructure import CodingStructure
+
+    p_pos = [n_frames - 1] if n_frames > 1 else []
+    cs = CodingStructure(n_frames=n_frames, intra_pos=[0], p_pos=p_pos)
+    v = VideoHeader()
+    v.set_header(n_frames, [0], p_pos)
+    out = v.to_bytes()
+    rng = np.random.default_rng(4321 + seed)
+    for coding_idx in range(n_frames):
+        fr = cs.get_frame_from_coding_order(coding_idx)
+        f = FrameHeader()
+        n_ref = len(fr.index_references)
+        gflow = [int(g) for g in rng.integers(-6, 7, size=2 * n_ref)]
+        f._values.update(display_index=fr.display_order, frame_type=fr.frame_type, frame_data_type=frame_data_type,
+                         bitdepth=bitdepth, index_references=list(fr.index_references), global_flow=gflow)
+        if n_ref:
+            f._values["warp_filter_size"] = warp_filter_size
+        out += f.to_bytes()
+        s = 100 * seed + coding_idx
+        if fr.frame_type == "I":
+            cc, _, _ = make_coolchic(ctx, seed_stream, (height, width), (0, 6), None, seed=s)
+            out += cc
+        else:
+            ov = {"spatial_context_arm": 10, "output_feature_ifce": 2}
+            ov.update(_syn_overrides(16, 3 + n_ref, 4))
+            cc, _, _ = make_coolchic(ctx, seed_stream, (height, width), (0, 6), None, seed=s, overrides=ov)
+            out += cc
+            ov = {"spatial_context_arm": 6, "output_feature_ifce": 2, "ifce_resolution": [2, 2]}
+            ov.update(_syn_overrides(16, 2 * n_ref, 2))
+            cc, _, _ = make_coolchic(ctx, seed_stream, (height, width), (2, 6), None, seed=s + 50,
+                                     final_upsampling_type="nearest", overrides=ov)
+            out += cc
+    return out

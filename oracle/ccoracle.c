@@ -1062,10 +1062,101 @@ int cco_finish_frame(const float *in, int h, int w, int bitdepth, int data_type,
     return CCO_OK;
 }
 
+/* ---- P/B prediction --------------------------------------------------------------------
+ * bitstream/decode.py:156-189.  apply_global_translation (globalmotion.py:151-160) is a
+ * grid_sample(nearest, border, align_corners=True) by an integer flow: an integer shift with
+ * border clamp.  Warper.forward (warp.py:294-397) runs in its TRAINING branch at decode time
+ * (SURVEY F5): no 1/64-pel flow quantisation; filter_size >= 6 -> windowed sinc (warp.py:226-268):
+ * integer part by clamped gathers, fractional part by N taps cos(pi(s-k)/N) * sinc(s-k),
+ * first along x (flow channel 0) for each of the N rows, then along y (flow channel 1).
+ * Coefficients are evaluated in double precision and rounded to fp32 (the reference does it
+ * in fp32: <= 1 ulp apart); products and sums are fp32, sequential, unfused.            */
+static void sinc_coeffs(float s, int n, float *c) {
+    const float PIf = 3.14159265358979323846f;
+    int lt = -(n / 2) + 1;
+    for (int k = 0; k < n; k++) {
+        float arg = s - (float)(lt + k);
+        float pa = PIf * arg;
+        double win = cos((double)(pa / (float)n));
+        double sc = (arg == 0.0f) ? 1.0 : sin((double)pa) / (double)pa;
+        c[k] = (float)win * (float)sc;
+    }
+}
+
+static void warp_sinc(const float *ref, int h, int w, int gx, int gy, const float *flow, int n, float *out) {
+    /* ref [3][h][w]; flow [2][h][w] (0: horizontal, 1: vertical); out [3][h][w] */
+    size_t plane = (size_t)h * w;
+    int lt = -(n / 2) + 1;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float fx = flow[(size_t)y * w + x], fy = flow[plane + (size_t)y * w + x];
+            float rx = floorf(fx), ry = floorf(fy);
+            float cx[16], cy[16];
+            sinc_coeffs(fx - rx, n, cx);
+            sinc_coeffs(fy - ry, n, cy);
+            int xs[16], ys[16];
+            for (int k = 0; k < n; k++) {
+                /* neighbour index clamped to the frame (warp.py:352-358), then the global
+                 * shift of the reference, clamped as well (globalmotion.py:154-155) */
+                float nx = (float)x + (float)(lt + k) + rx, ny = (float)y + (float)(lt + k) + ry;
+                nx = nx < 0.0f ? 0.0f : (nx > (float)(w - 1) ? (float)(w - 1) : nx);
+                ny = ny < 0.0f ? 0.0f : (ny > (float)(h - 1) ? (float)(h - 1) : ny);
+                xs[k] = clampi((int)nx + gx, 0, w - 1);
+                ys[k] = clampi((int)ny + gy, 0, h - 1);
+            }
+            for (int c = 0; c < 3; c++) {
+                const float *p = ref + (size_t)c * plane;
+                float col = 0.0f;
+                for (int i = 0; i < n; i++) {
+                    float line = 0.0f;
+                    for (int j = 0; j < n; j++) {
+                        float t = p[(size_t)ys[i] * w + xs[j]] * cx[j];
+                        line = (j == 0) ? t : line + t;
+                    }
+                    float t2 = line * cy[i];
+                    col = (i == 0) ? t2 : col + t2;
+                }
+                out[(size_t)c * plane + (size_t)y * w + x] = col;
+            }
+        }
+}
+
 int cco_inter_predict(const float *residue, const float *motion, const float *ref0,
                       const float *ref1, int h, int w, int is_b, const int32_t *global_flow,
                       int warp_filter_size, float *out) {
-    (void)residue; (void)motion; (void)ref0; (void)ref1; (void)h; (void)w; (void)is_b;
-    (void)global_flow; (void)warp_filter_size; (void)out;
-    return CCO_ERR_UNSUPPORTED;
+    if (warp_filter_size < 6 || (warp_filter_size & 1) || warp_filter_size > 16) return CCO_ERR_UNSUPPORTED;
+    size_t plane = (size_t)h * w;
+    float *w0 = (float *)malloc(plane * 3 * 4 + 16), *w1 = NULL;
+    if (!w0) return CCO_ERR_NOMEM;
+    warp_sinc(ref0, h, w, global_flow[0], global_flow[1], motion, warp_filter_size, w0);
+    if (is_b) {
+        w1 = (float *)malloc(plane * 3 * 4 + 16);
+        if (!w1) {
+            free(w0);
+            return CCO_ERR_NOMEM;
+        }
+        warp_sinc(ref1, h, w, global_flow[2], global_flow[3], motion + 2 * plane, warp_filter_size, w1);
+    }
+    for (size_t i = 0; i < plane; i++) {
+        float a = residue[3 * plane + i] + 0.5f;
+        a = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);
+        float b = 0.0f;
+        if (is_b) {
+            b = residue[4 * plane + i] + 0.5f;
+            b = b < 0.0f ? 0.0f : (b > 1.0f ? 1.0f : b);
+        }
+        for (int c = 0; c < 3; c++) {
+            float pred = w0[c * plane + i];
+            if (is_b) {
+                float t1 = b * pred, t2 = (1.0f - b) * w1[c * plane + i];
+                pred = t1 + t2;
+            }
+            float m = a * pred;
+            out[c * plane + i] = m + residue[c * plane + i];
+        }
+    }
+    free(w0);
+    free(w1);
+    return CCO_OK;
 }

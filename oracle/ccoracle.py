@@ -176,3 +176,20 @@ def laplace_domain(sc_lo: int, sc_hi: int):
 def set_threads(n: int = 0) -> int:
     """Threads used by the float tail (0 = leave as is / all cores); returns the count."""
     return int(lib().cco_set_threads(n))
+
+
+def inter_predict(residue, motion, ref0, ref1, global_flow, warp_filter_size):
+    """decode_frame P/B branch before rounding.  residue [4|5,H,W], motion [2|4,H,W], refs [3,H,W]."""
+    residue = np.ascontiguousarray(residue, dtype=np.float32)
+    motion = np.ascontiguousarray(motion, dtype=np.float32)
+    ref0 = np.ascontiguousarray(ref0, dtype=np.float32)
+    is_b = ref1 is not None
+    if is_b:
+        ref1 = np.ascontiguousarray(ref1, dtype=np.float32)
+    _, h, w = ref0.shape
+    gf = np.zeros(4, dtype=np.int32)
+    gf[: len(global_flow)] = global_flow
+    out = np.zeros((3, h, w), dtype=np.float32)
+    _chk(lib().cco_inter_predict(_p(residue), _p(motion), _p(ref0), _p(ref1) if is_b else None, h, w, int(is_b),
+                                 _p(gf), int(warp_filter_size), _p(out)), "inter_predict")
+    return out

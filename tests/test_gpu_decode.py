@@ -239,3 +239,101 @@ def test_full_size_round_trip(ctx, oracle, seed_stream, hw, lr):
         # (9 s); checksum of checksums instead: per-channel sums are finite and non-trivial
         s = out.double().sum(dim=(2, 3)).cpu().numpy()
         assert np.all(np.abs(s) > 1.0)
+
+
+# ------------------------------------------------------------------------------------------
+# P/B frames
+TOL_INTER = 1e-6  # sinc coefficients go through device / host double-precision cos, sin
+
+
+@pytest.mark.parametrize("is_b,fs", [(False, 8), (True, 8), (True, 6), (False, 12)])
+def test_inter_predict_vs_oracle(ctx, oracle, is_b, fs):
+    import torch
+
+    from coolchic_b200.io import FrameData
+
+    rng = np.random.default_rng(11)
+    h, w = 45, 70
+    residue = rng.normal(0, 0.3, size=(5 if is_b else 4, h, w)).astype(np.float32)
+    motion = rng.normal(0, 3.0, size=(4 if is_b else 2, h, w)).astype(np.float32)
+    motion[0, :4, :4] = np.array([[0.0, 1.0, -1.0, 2.5]] * 4)  # integer and half-pel flows
+    motion[:, 0, 0] = 500.0                                     # far outside the frame: border clamp
+    ref0 = rng.uniform(0, 1, size=(3, h, w)).astype(np.float32)
+    ref1 = rng.uniform(0, 1, size=(3, h, w)).astype(np.float32)
+    gf = [3, -2, -5, 4] if is_b else [6, 1]
+    want = oracle.inter_predict(residue, motion, ref0, ref1 if is_b else None, gf, fs)
+    refs = [FrameData(8, "rgb", torch.from_numpy(ref0[None]).cuda())]
+    if is_b:
+        refs.append(FrameData(8, "rgb", torch.from_numpy(ref1[None]).cuda()))
+    got = ctx.inter_predict(torch.from_numpy(residue[None]).cuda(), torch.from_numpy(motion[None]).cuda(), refs, is_b,
+                            "rgb", gf, fs)
+    assert np.abs(got[0].cpu().numpy() - want).max() <= TOL_INTER
+
+
+def test_unsupported_warp_is_an_error_not_a_fallback(ctx):
+    import torch
+
+    from coolchic_b200 import _native
+    from coolchic_b200.io import FrameData
+
+    z = torch.zeros((1, 4, 8, 8), device="cuda")
+    with pytest.raises(_native.CcdError) as e:
+        ctx.inter_predict(z, z[:, :2].contiguous(), [FrameData(8, "rgb", z[:, :3].contiguous())], False, "rgb", [0, 0], 4)
+    assert e.value.code == -4  # CCD_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name,fmt", [("gop5_64x96_yuv420", "yuv420"), ("gop3_40x56_rgb", "rgb")])
+def test_gop_decode_video(ctx, name, fmt, tmp_path):
+    """decode_video on a P/B stream against frames decoded by the UNMODIFIED reference."""
+    from coolchic_b200.bitstream.decode import decode_video
+
+    path = os.path.join(GOLDEN, name + ".cool")
+    gold = np.load(os.path.join(GOLDEN, name + "_frames.npz"))
+    out = str(tmp_path / ("o.yuv" if fmt == "yuv420" else "o.ppm"))
+    frames = decode_video(path, decoded_path=out if fmt == "yuv420" else None)
+    n = len(frames)
+    assert sorted(frames) == sorted(str(i) for i in range(n))
+    bad = tot = 0
+    for k, fd in frames.items():
+        assert fd.frame_data_type == fmt and fd.bitdepth == 8
+        if fmt == "yuv420":
+            for c in "yuv":
+                a = np.round(fd.data[c][0, 0].numpy() * 255).astype(np.int32)
+                b = gold[f"{k}_{c}"].astype(np.int32)
+                assert np.abs(a - b).max() <= 1
+                bad += int((a != b).sum())
+                tot += a.size
+        else:
+            a = np.round(fd.data[0].numpy() * 255).astype(np.int32)
+            b = gold[k].astype(np.int32)
+            assert np.abs(a - b).max() <= 1
+            bad += int((a != b).sum())
+            tot += a.size
+    assert bad <= max(4, tot // 2000)  # rounding ties only
+    if fmt == "yuv420":
+        assert os.path.getsize(out) == n * (64 * 96 * 3 // 2)  # planar frames appended in display order
+
+
+def test_gop_1080p_yuv420_properties(ctx, seed_stream):
+    """BASELINE config 5 shape (1080p YUV420 GOP with sinc-8 warps), 3 frames: decodes, values on the 8-bit grid."""
+    import torch
+
+    from coolchic_b200 import synth
+    from coolchic_b200.bitstream.decode import decode_frame
+    from coolchic_b200.bitstream.header import VideoHeader
+
+    data = synth.make_video_stream(ctx, seed_stream, 1080, 1920, 3, "yuv420", 8, 8, seed=2)
+    v = VideoHeader()
+    rest = v.read_header(data)
+    cs = v.get_coding_structure()
+    for coding_idx in range(3):
+        fr = cs.get_frame_from_coding_order(coding_idx)
+        refs = [cs.get_frame_from_display_order(i).data for i in fr.index_references]
+        fd, rest = decode_frame(rest, refs)
+        fr.set_frame_data(fd)
+        for c, shape in (("y", (1080, 1920)), ("u", (540, 960)), ("v", (540, 960))):
+            t = fd.data[c]
+            assert tuple(t.shape[-2:]) == shape and torch.isfinite(t).all()
+            lv = t * 255
+            assert float((lv - torch.round(lv)).abs().max()) < 1e-3 and float(t.min()) >= 0 and float(t.max()) <= 1
+    assert rest == b""
