@@ -745,12 +745,18 @@ __device__ __noinline__ FarOut coder_far(const SmemLayout &sm, const float *__re
 // LM = (left(mode), left(mode + 1)): the most probable symbol is tested speculatively.
 __device__ __forceinline__ void coder_step(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
                                            uint32_t ring_mask, int lane, uint32_t j, uint2 LM, uint64_t &D,
-                                           uint64_t &R, uint32_t &wnext, DecState &c) {
+                                           uint64_t &R, uint32_t &wnext, DecState &c, ProfCounters &pc) {
     const uint64_t scale = R >> 24;
     uint64_t lo = scale * LM.x, hi = scale * LM.y;
     uint32_t rw = res_word(j, (uint32_t)CCD_WIN_HALF, false);
     if (!((lo <= D) && (D < hi))) {
+        PROF_T(tf);
         const FarOut f = coder_far(sm, scale_tab, ring_mask, lane, j, scale, D, &c.slow, &c.err);
+#ifdef CCD_PROFILE
+        pc.seg[1]++;
+        if (f.rw == 0xffffffffu) pc.seg[5]++;
+        pc.seg[2] += clock64() - tf;
+#endif
         lo = f.lo;
         hi = f.hi;
         rw = f.rw;
@@ -808,22 +814,22 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
                     if ((int32_t)(limit - j) < 6) break;
                 }
                 const uint2 b0 = mode_of(j + 3u), b1 = mode_of(j + 4u), b2 = mode_of(j + 5u);
-                coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c);
-                coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c);
-                coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c);
+                coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c, pc);
+                coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c, pc);
+                coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c, pc);
                 j += 3u;
                 a0 = b0;
                 a1 = b1;
                 a2 = b2;
             }
             // a0..a2 are valid (limit - j >= 3 here)
-            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c);
-            coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c);
-            coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c, pc);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c, pc);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c, pc);
             j += 3u;
         } else {
             const uint2 a0 = mode_of(j);
-            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c);
+            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c, pc);
             j++;
         }
     }
@@ -1056,9 +1062,7 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
             atomicAdd(&G.status[5], (int)(pc.total >> 10));
             G.status[10] = (int)pc.seg[0];
             G.status[11] = (int)pc.seg[1];
-            G.status[12] = (int)pc.seg[2];
-            G.status[13] = (int)(pc.seg[3] >> 4);
-            G.status[14] = (int)(pc.seg[4] >> 4);
+            G.status[12] = (int)(pc.seg[2] >> 10);
         }
     }
 #endif

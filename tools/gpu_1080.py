@@ -1,0 +1,24 @@
+"""Development tool: 1080p synthetic stream: timings + entropy-kernel status / profile counters."""
+import os, sys, time
+import numpy as np, torch
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+import coolchic_b200
+from coolchic_b200 import _native, synth
+from coolchic_b200._desc import desc_from_header
+ctx = _native.get_context(0)
+ss = synth.SeedStream(ctx)
+hyp = (4, 6) if len(sys.argv) > 1 and sys.argv[1] == "hyper" else None
+cc, h, lat = synth.make_coolchic(ctx, ss, (1080, 1920), (0, 6), hyp, seed=0)
+h2 = type(h)(); rest = h2.read_header(cc); d = desc_from_header(h2)
+nnb = rest[:h2.get_value("nn_n_bytes")]; lb = rest[h2.get_value("nn_n_bytes"):][:h2.get_value("n_bytes_latent")]
+nn = _native.decode_nn(d, nnb)
+print("symbols", d.n_symbols(), "payload", len(lb), "bpp %.3f" % (len(lb) * 8 / (1080 * 1920)))
+for it in range(3):
+    out = ctx.decode_latents(d, nn, lb); torch.cuda.synchronize()
+    print(ctx.last_timing(), ctx.last_status())
+print("round trip ok:", torch.equal(out, lat))
+l = lat.cpu().numpy().astype(int); off = 0
+for g in range(d.n_grids - 1, -1, -1):
+    n = d.grid_h[g] * d.grid_w[g]; a = l[off:off + n]; off += n
+    print("grid", g, (d.grid_h[g], d.grid_w[g]), "zeros %.2f mean|x| %.2f max %d" % ((a == 0).mean(), np.abs(a).mean(), np.abs(a).max()))
