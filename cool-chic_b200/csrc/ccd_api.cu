@@ -1022,14 +1022,12 @@ int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_mo
                       float *d_out, void *cuda_stream) {
     if (!ctx || !d_residue || !d_motion || !d_ref0 || !d_out || !global_flow || h < 2 || w < 2 || (is_b && !d_ref1))
         return fail(CCD_ERR_ARG, "bad argument");
-    if (warp_filter_size == 2 || warp_filter_size == 4)
-        return fail(CCD_ERR_UNSUPPORTED, "bilinear / bicubic warps (filter_size 2, 4) are not implemented yet");
-    if (warp_filter_size < 6 || (warp_filter_size & 1)) return fail(CCD_ERR_ARG, "bad warp filter size %d", warp_filter_size);
+    if (warp_filter_size < 2 || (warp_filter_size & 1)) return fail(CCD_ERR_ARG, "bad warp filter size %d", warp_filter_size);
     CUDA_TRY(cudaSetDevice(ctx->device));
     int32_t gf[4] = {global_flow[0], global_flow[1], is_b ? global_flow[2] : 0, is_b ? global_flow[3] : 0};
     int rc = ccd_inter_launch(d_residue, d_motion, d_ref0, d_ref1, h, w, is_b, gf, warp_filter_size, d_out,
                               (cudaStream_t)cuda_stream);
-    if (rc == -1) return fail(CCD_ERR_UNSUPPORTED, "warp filter size %d is not instantiated (6, 8, 10, 12 are)", warp_filter_size);
+    if (rc == -1) return fail(CCD_ERR_UNSUPPORTED, "warp filter size %d is not instantiated (2, 4, 6, 8, 10, 12 are; 2 and 4 need a frame of at least 2x2)", warp_filter_size);
     if (rc) return fail(CCD_ERR_CUDA, "inter_predict launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     return CCD_OK;
 }

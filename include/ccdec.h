@@ -157,8 +157,9 @@ int ccd_finish_frame(CcdContext *ctx, const float *d_in, int h, int w, int bitde
  * globalmotion.py:151-160, Warper.forward warp.py:294-397 in its training branch, alpha/beta
  * blending).  d_residue [4|5][H][W], d_motion [2|4][H][W]: raw synthesis outputs;
  * d_ref0/d_ref1 [3][H][W] (444).  global_flow: (x,y) per reference.  d_out [3][H][W]
- * pre-rounding frame (feed to ccd_finish_frame).  Implemented: windowed-sinc warps
- * (warp_filter_size 6, 8, 10, 12); sizes 2 / 4 (bilinear / bicubic) return CCD_ERR_UNSUPPORTED. */
+ * pre-rounding frame (feed to ccd_finish_frame).  warp_filter_size 2 / 4: grid_sample bilinear /
+ * bicubic (border, align_corners); 6, 8, 10, 12: windowed sinc; other even sizes return
+ * CCD_ERR_UNSUPPORTED (not instantiated). */
 int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_motion,
                       const float *d_ref0, const float *d_ref1, int h, int w, int is_b,
                       const int32_t *global_flow, int warp_filter_size, float *d_out,

@@ -1122,21 +1122,112 @@ static void warp_sinc(const float *ref, int h, int w, int gx, int gy, const floa
         }
 }
 
+/* filter_size 2 / 4: WarpParameter picks "torch_bilinear" / "torch_bicubic" (warp.py:50-56), i.e.
+ * F.grid_sample(padding_mode="border", align_corners=True) on backward_grid + flow / ((size-1)/2)
+ * (warp.py:92-111, 314-334).  Restated from PyTorch's CPU kernels:
+ *  - torch.linspace(-1, 1, n) (RangeFactoriesKernel.cpp): step = 2/(n-1) in fp32;
+ *    i < n/2 ? fma(step, i, -1) : fma(-step, n-1-i, 1)   (checked == torch for n = 2..400, 768..4096)
+ *  - unnormalise: (g + 1) * ((size-1)/2); border: clip to [0, size-1] (GridSamplerKernel.cpp)
+ *  - bilinear: weights s*e, s*w, n*e, n*w; value = fma chain nw -> ne -> sw -> se (bit-exact with
+ *    torch 2.11 on random inputs, oracle/gen_golden_gop.py)
+ *  - bicubic: A = -0.75 cubic convolution coefficients of t = x - floor(x) (unclipped), each of the
+ *    4x4 taps clipped to the frame; within 2e-7 of torch (its exact contraction pattern is
+ *    compiler dependent). */
+static float lin_coord(int n, int i) {
+    float step = 2.0f / (float)(n - 1);
+    return (i < n / 2) ? fmaf(step, (float)i, -1.0f) : fmaf(-step, (float)(n - 1 - i), 1.0f);
+}
+static float cubic_near(float x) { /* |x| <= 1: ((A+2)x - (A+3)) x x + 1 */
+    float a = 1.25f * x - 2.25f;
+    float b = a * x;
+    return fmaf(b, x, 1.0f);
+}
+static float cubic_far(float x) { /* 1 < |x| < 2: ((Ax - 5A) x + 8A) x - 4A */
+    float a = -0.75f * x + 3.75f;
+    float b = a * x + -6.0f;
+    return b * x + 3.0f;
+}
+static void warp_grid(const float *ref, int h, int w, int gx, int gy, const float *flow, int n, float *out) {
+    size_t plane = (size_t)h * w;
+    const float sx = (float)((w - 1.0) / 2.0), sy = (float)((h - 1.0) / 2.0);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float fx = flow[(size_t)y * w + x], fy = flow[plane + (size_t)y * w + x];
+            float g0 = lin_coord(w, x) + fx / sx, g1 = lin_coord(h, y) + fy / sy;
+            float ix = (g0 + 1.0f) * sx, iy = (g1 + 1.0f) * sy;
+            if (n == 2) {
+                ix = fminf((float)(w - 1), fmaxf(ix, 0.0f));
+                iy = fminf((float)(h - 1), fmaxf(iy, 0.0f));
+                float xw = floorf(ix), yn = floorf(iy);
+                float ww = ix - xw, e = 1.0f - ww, nn = iy - yn, s = 1.0f - nn;
+                float k_nw = s * e, k_ne = s * ww, k_sw = nn * e, k_se = nn * ww;
+                int x0 = (int)xw, y0 = (int)yn, x1 = x0 + 1, y1 = y0 + 1;
+                int xa = clampi(x0 + gx, 0, w - 1), xb = clampi((x1 < w ? x1 : w - 1) + gx, 0, w - 1);
+                int ya = clampi(y0 + gy, 0, h - 1), yb = clampi((y1 < h ? y1 : h - 1) + gy, 0, h - 1);
+                for (int c = 0; c < 3; c++) {
+                    const float *p = ref + (size_t)c * plane;
+                    float v00 = p[(size_t)ya * w + xa];
+                    float v01 = x1 < w ? p[(size_t)ya * w + xb] : 0.0f;
+                    float v10 = y1 < h ? p[(size_t)yb * w + xa] : 0.0f;
+                    float v11 = (x1 < w && y1 < h) ? p[(size_t)yb * w + xb] : 0.0f;
+                    float r = v00 * k_nw;
+                    r = fmaf(v01, k_ne, r);
+                    r = fmaf(v10, k_sw, r);
+                    r = fmaf(v11, k_se, r);
+                    out[(size_t)c * plane + (size_t)y * w + x] = r;
+                }
+            } else {
+                float fxx = floorf(ix), fyy = floorf(iy);
+                float tx = ix - fxx, ty = iy - fyy;
+                float cx[4] = {cubic_far(tx + 1.0f), cubic_near(tx), cubic_near(1.0f - tx), cubic_far(2.0f - tx)};
+                float cy[4] = {cubic_far(ty + 1.0f), cubic_near(ty), cubic_near(1.0f - ty), cubic_far(2.0f - ty)};
+                int xs[4], ys[4];
+                for (int k = 0; k < 4; k++) {
+                    float nx = fminf((float)(w - 1), fmaxf(fxx + (float)(k - 1), 0.0f));
+                    float ny = fminf((float)(h - 1), fmaxf(fyy + (float)(k - 1), 0.0f));
+                    xs[k] = clampi((int)nx + gx, 0, w - 1);
+                    ys[k] = clampi((int)ny + gy, 0, h - 1);
+                }
+                for (int c = 0; c < 3; c++) {
+                    const float *p = ref + (size_t)c * plane;
+                    float rows[4];
+                    for (int i = 0; i < 4; i++) {
+                        const float *q = p + (size_t)ys[i] * w;
+                        float r = cx[0] * q[xs[0]];
+                        r = fmaf(cx[1], q[xs[1]], r);
+                        r = fmaf(cx[2], q[xs[2]], r);
+                        r = fmaf(cx[3], q[xs[3]], r);
+                        rows[i] = r;
+                    }
+                    float a = cy[0] * rows[0];
+                    a = fmaf(cy[1], rows[1], a);
+                    a = fmaf(cy[2], rows[2], a);
+                    a = fmaf(cy[3], rows[3], a);
+                    out[(size_t)c * plane + (size_t)y * w + x] = a;
+                }
+            }
+        }
+}
+
 int cco_inter_predict(const float *residue, const float *motion, const float *ref0,
                       const float *ref1, int h, int w, int is_b, const int32_t *global_flow,
                       int warp_filter_size, float *out) {
-    if (warp_filter_size < 6 || (warp_filter_size & 1) || warp_filter_size > 16) return CCO_ERR_UNSUPPORTED;
+    if (warp_filter_size < 2 || (warp_filter_size & 1) || warp_filter_size > 16) return CCO_ERR_UNSUPPORTED;
+    if (warp_filter_size < 6 && (h < 2 || w < 2)) return CCO_ERR_UNSUPPORTED;
     size_t plane = (size_t)h * w;
     float *w0 = (float *)malloc(plane * 3 * 4 + 16), *w1 = NULL;
     if (!w0) return CCO_ERR_NOMEM;
-    warp_sinc(ref0, h, w, global_flow[0], global_flow[1], motion, warp_filter_size, w0);
+    void (*warp)(const float *, int, int, int, int, const float *, int, float *) =
+        warp_filter_size < 6 ? warp_grid : warp_sinc;
+    warp(ref0, h, w, global_flow[0], global_flow[1], motion, warp_filter_size, w0);
     if (is_b) {
         w1 = (float *)malloc(plane * 3 * 4 + 16);
         if (!w1) {
             free(w0);
             return CCO_ERR_NOMEM;
         }
-        warp_sinc(ref1, h, w, global_flow[2], global_flow[3], motion + 2 * plane, warp_filter_size, w1);
+        warp(ref1, h, w, global_flow[2], global_flow[3], motion + 2 * plane, warp_filter_size, w1);
     }
     for (size_t i = 0; i < plane; i++) {
         float a = residue[3 * plane + i] + 0.5f;

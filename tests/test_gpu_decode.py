@@ -246,7 +246,8 @@ def test_full_size_round_trip(ctx, oracle, seed_stream, hw, lr):
 TOL_INTER = 1e-6  # sinc coefficients go through device / host double-precision cos, sin
 
 
-@pytest.mark.parametrize("is_b,fs", [(False, 8), (True, 8), (True, 6), (False, 12)])
+@pytest.mark.parametrize("is_b,fs", [(False, 8), (True, 8), (True, 6), (False, 12), (False, 2), (True, 2), (False, 4),
+                                      (True, 4)])
 def test_inter_predict_vs_oracle(ctx, oracle, is_b, fs):
     import torch
 
@@ -278,11 +279,12 @@ def test_unsupported_warp_is_an_error_not_a_fallback(ctx):
 
     z = torch.zeros((1, 4, 8, 8), device="cuda")
     with pytest.raises(_native.CcdError) as e:
-        ctx.inter_predict(z, z[:, :2].contiguous(), [FrameData(8, "rgb", z[:, :3].contiguous())], False, "rgb", [0, 0], 4)
-    assert e.value.code == -4  # CCD_ERR_UNSUPPORTED
+        ctx.inter_predict(z, z[:, :2].contiguous(), [FrameData(8, "rgb", z[:, :3].contiguous())], False, "rgb", [0, 0], 14)
+    assert e.value.code == -4  # CCD_ERR_UNSUPPORTED: sinc-14 is not instantiated
 
 
-@pytest.mark.parametrize("name,fmt", [("gop5_64x96_yuv420", "yuv420"), ("gop3_40x56_rgb", "rgb")])
+@pytest.mark.parametrize("name,fmt", [("gop5_64x96_yuv420", "yuv420"), ("gop3_40x56_rgb", "rgb"),
+                                      ("gop3_48x72_yuv420_bilinear", "yuv420"), ("gop3_40x56_rgb_bicubic", "rgb")])
 def test_gop_decode_video(ctx, name, fmt, tmp_path):
     """decode_video on a P/B stream against frames decoded by the UNMODIFIED reference."""
     from coolchic_b200.bitstream.decode import decode_video
@@ -311,7 +313,8 @@ def test_gop_decode_video(ctx, name, fmt, tmp_path):
             tot += a.size
     assert bad <= max(4, tot // 2000)  # rounding ties only
     if fmt == "yuv420":
-        assert os.path.getsize(out) == n * (64 * 96 * 3 // 2)  # planar frames appended in display order
+        h, w = frames["0"].data["y"].shape[-2:]
+        assert os.path.getsize(out) == n * (h * w * 3 // 2)  # planar frames appended in display order
 
 
 def test_gop_1080p_yuv420_properties(ctx, seed_stream):
