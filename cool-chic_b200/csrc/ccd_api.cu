@@ -580,6 +580,54 @@ int prepare_job(PreparedJob &P, const int64_t *nn_ints_opt) {
     return CCD_OK;
 }
 
+// Device scratch of the float tail of one job.
+struct SynScratch {
+    size_t off_nxt = 0, off_a = 0, off_b = 0, off_stab = 0, off_noise_raw = 0, off_noise_a = 0, off_noise_b = 0, total = 0;
+    std::vector<int> fused;  // layer l is evaluated together with l + 1 (two 1x1 layers)
+};
+SynScratch syn_scratch_plan(const CcdCoolChicDesc *d) {
+    SynScratch S;
+    int nl = 0, g0 = -1;
+    for (int g = 0; g < d->n_grids; g++)
+        if (!d->grid_is_hyper[g]) {
+            if (g0 < 0) g0 = g;
+            nl++;
+        }
+    S.fused.assign((size_t)std::max(d->n_syn_layers, 1), 0);
+    if (g0 < 0 || d->n_syn_layers < 1) return S;
+    const size_t plane = (size_t)d->grid_h[g0] * d->grid_w[g0];
+    const int C = d->syn_out[d->n_syn_layers - 1];
+    int maxc = std::max(d->syn_in, C);
+    int in_ft = d->syn_in;
+    for (int l = 0; l < d->n_syn_layers; l++) {
+        const bool can = l + 1 < d->n_syn_layers && d->syn_k[l] == 1 && d->syn_k[l + 1] == 1 && !d->syn_res[l] &&
+                         !d->syn_res[l + 1] && in_ft <= 16 && d->syn_out[l + 1] <= 8;
+        if (can) {
+            S.fused[(size_t)l] = 1;
+            maxc = std::max(maxc, d->syn_out[l + 1]);
+            in_ft = d->syn_out[l + 1];
+            l++;
+        } else {
+            maxc = std::max(maxc, d->syn_out[l]);
+            in_ft = d->syn_out[l];
+        }
+    }
+    const size_t dense = al(plane * (size_t)(std::max(nl, d->syn_in) + 1) * 4);
+    const size_t trunk = al(plane * (size_t)maxc * 4);
+    size_t p = dense;
+    S.off_nxt = p; p += dense;
+    S.off_a = p; p += trunk;
+    S.off_b = p; p += trunk;
+    S.off_stab = p; p += al(plane * (size_t)C * 4);
+    if (d->common_randomness) {
+        S.off_noise_raw = p; p += al(plane * 2 * 4 + (size_t)nl * 64);  // sum of ceil(H/2^i) ceil(W/2^i) <= 2 plane
+        S.off_noise_a = p; p += al(plane * (size_t)nl * 4);
+        S.off_noise_b = p; p += al(plane * (size_t)nl * 4);
+    }
+    S.total = p;
+    return S;
+}
+
 void expand_sym(const float *par, int k, float *full) {
     // _Parameterization_Symmetric_1d (core/upsampling.py:42-64): a b c d -> a b c d [d] c b a
     const int np = (k + 1) / 2;
@@ -592,40 +640,25 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
                   unsigned char *scratch, size_t scratch_bytes, cudaStream_t st) {
     const CcdCoolChicDesc *d = P.d;
     const NNLayout &L = P.L;
-    if (d->common_randomness) return fail(CCD_ERR_UNSUPPORTED, "common randomness streams are not supported yet");
+    const int cr = d->common_randomness != 0;
     int gl[CCD_MAX_GRIDS], nl = 0;
     for (int g = 0; g < d->n_grids; g++)
         if (!d->grid_is_hyper[g]) gl[nl++] = g;
-    if (nl != d->syn_in || nl < 1) return fail(CCD_ERR_ARG, "synthesis input width %d != %d latent grids", d->syn_in, nl);
+    if (nl * (cr ? 2 : 1) != d->syn_in || nl < 1)
+        return fail(CCD_ERR_ARG, "synthesis input width %d does not match %d latent grids", d->syn_in, nl);
     const int h0 = d->grid_h[gl[0]], w0 = d->grid_w[gl[0]];
+    if (cr && (h0 != d->img_h || w0 != d->img_w || nl != d->latent_res_hi - d->latent_res_lo + 1))
+        return fail(CCD_ERR_ARG, "common randomness needs a full-resolution finest latent grid");
     const size_t plane = (size_t)h0 * w0;
     const int C = L.syn_c;
-    int maxc = std::max(d->syn_in, C);
-    // which layers get materialised? (pairs of 1x1 layers are fused)
-    std::vector<int> fused((size_t)d->n_syn_layers, 0);
-    {
-        int in_ft = d->syn_in;
-        for (int l = 0; l < d->n_syn_layers; l++) {
-            const bool can = l + 1 < d->n_syn_layers && d->syn_k[l] == 1 && d->syn_k[l + 1] == 1 && !d->syn_res[l] &&
-                             !d->syn_res[l + 1] && in_ft <= 16 && d->syn_out[l + 1] <= 8;
-            if (can) {
-                fused[(size_t)l] = 1;
-                maxc = std::max(maxc, d->syn_out[l + 1]);
-                in_ft = d->syn_out[l + 1];
-                l++;
-            } else {
-                maxc = std::max(maxc, d->syn_out[l]);
-                in_ft = d->syn_out[l];
-            }
-        }
-    }
-    const size_t need = al(plane * (size_t)(nl + 1) * 4) * 2 + al(plane * (size_t)maxc * 4) * 2 + al(plane * (size_t)C * 4);
-    if (need > scratch_bytes) return fail(CCD_ERR_NOMEM, "internal: scratch too small (%zu > %zu)", need, scratch_bytes);
+    const SynScratch SS = syn_scratch_plan(d);
+    if (SS.total > scratch_bytes) return fail(CCD_ERR_NOMEM, "internal: scratch too small (%zu > %zu)", SS.total, scratch_bytes);
+    const std::vector<int> &fused = SS.fused;
     float *cur = reinterpret_cast<float *>(scratch);
-    float *nxt = reinterpret_cast<float *>(scratch + al(plane * (size_t)(nl + 1) * 4));
-    float *bufa = reinterpret_cast<float *>(scratch + 2 * al(plane * (size_t)(nl + 1) * 4));
-    float *bufb = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bufa) + al(plane * (size_t)maxc * 4));
-    float *stab = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bufb) + al(plane * (size_t)maxc * 4));
+    float *nxt = reinterpret_cast<float *>(scratch + SS.off_nxt);
+    float *bufa = reinterpret_cast<float *>(scratch + SS.off_a);
+    float *bufb = reinterpret_cast<float *>(scratch + SS.off_b);
+    float *stab = reinterpret_cast<float *>(scratch + SS.off_stab);
 
     const float qs_uw = ldexpf(1.0f, d->qshift[4]);
     int gc = gl[nl - 1];
@@ -650,6 +683,47 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
         ch = th;
         cw = tw;
         cc++;
+    }
+    if (cr) {
+        // bitstream/component/coolchic.py:179-183: noise grids (noise.py) -> fixed_upsampling(bicubic)
+        // (upsampling.py:556-595) -> channels nl .. 2 nl - 1 of the synthesis input
+        float *raw = reinterpret_cast<float *>(scratch + SS.off_noise_raw);
+        float *na = reinterpret_cast<float *>(scratch + SS.off_noise_a);
+        float *nb = reinterpret_cast<float *>(scratch + SS.off_noise_b);
+        int gh[CCD_MAX_GRIDS], gw[CCD_MAX_GRIDS];
+        size_t goff[CCD_MAX_GRIDS], tot = 0;
+        for (int i = 0; i < nl; i++) {
+            const int sh = d->latent_res_lo + i;
+            gh[i] = (int)((d->img_h + (1LL << sh) - 1) >> sh);
+            gw[i] = (int)((d->img_w + (1LL << sh) - 1) >> sh);
+            goff[i] = tot;
+            tot += (size_t)gh[i] * gw[i];
+        }
+        if (ccd_cr_noise(raw, 0, tot, st)) return fail(CCD_ERR_CUDA, "noise launch");
+        int nh = gh[nl - 1], nw = gw[nl - 1], nc = 1;
+        const float *ncur = raw + goff[nl - 1];
+        for (int i = nl - 2; i >= 0; i--) {
+            const int th = gh[i], tw = gw[i];
+            float *dstp = (i == 0) ? cur + plane * (size_t)nl : ((ncur == na) ? nb : na);
+            if (th > 2 * nh || tw > 2 * nw) return fail(CCD_ERR_ARG, "noise grid %d more than twice its parent", i);
+            if (cudaMemcpyAsync(dstp, raw + goff[i], (size_t)th * tw * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                return fail(CCD_ERR_CUDA, "noise copy");
+            if (th != nh || tw != nw) {
+                if (ccd_resize_torch(ncur, nc, nh, nw, dstp + (size_t)th * tw, th, tw, 2, 0.5f, 0.5f, st))
+                    return fail(CCD_ERR_CUDA, "noise upsampling launch");
+            } else if (cudaMemcpyAsync(dstp + (size_t)th * tw, ncur, (size_t)nc * nh * nw * 4, cudaMemcpyDeviceToDevice,
+                                       st) != cudaSuccess) {
+                return fail(CCD_ERR_CUDA, "noise copy");
+            }
+            ncur = dstp;
+            nh = th;
+            nw = tw;
+            nc++;
+        }
+        if (nl == 1 &&
+            cudaMemcpyAsync(cur + plane, raw, plane * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            return fail(CCD_ERR_CUDA, "noise copy");
+        // gh[0] x gw[0] == image size here, so the final bicubic interpolate is the identity
     }
     // ---- synthesis (core/synthesis.py:272-294)
     auto layer = [&](int l, int cin) {
@@ -694,47 +768,18 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
     if ((rc = ccd_syn_layer(trunk, h0, w0, Lo, ot_dst, st))) return fail(CCD_ERR_CUDA, "output transform launch");
     if (!same) {
         // final F.interpolate (component/coolchic.py:187-192)
-        if (d->final_ups != 0) return fail(CCD_ERR_UNSUPPORTED, "final bilinear/bicubic resize is not supported yet");
-        if ((rc = ccd_resize_nearest(ot_dst, C, h0, w0, d_out, d->img_h, d->img_w, st)))
-            return fail(CCD_ERR_CUDA, "resize launch");
+        if (d->final_ups == 0)
+            rc = ccd_resize_nearest(ot_dst, C, h0, w0, d_out, d->img_h, d->img_w, st);
+        else
+            rc = ccd_resize_torch(ot_dst, C, h0, w0, d_out, d->img_h, d->img_w, d->final_ups == 1 ? 1 : 2,
+                                  (float)h0 / (float)d->img_h, (float)w0 / (float)d->img_w, st);
+        if (rc) return fail(CCD_ERR_CUDA, "resize launch");
     }
     (void)ctx;
     return CCD_OK;
 }
 
-size_t synthesis_scratch_bytes(const CcdCoolChicDesc *d) {
-    int nl = 0, g0 = -1;
-    for (int g = 0; g < d->n_grids; g++)
-        if (!d->grid_is_hyper[g]) {
-            if (g0 < 0) g0 = g;
-            nl++;
-        }
-    if (g0 < 0) return 0;
-    const size_t plane = (size_t)d->grid_h[g0] * d->grid_w[g0];
-    int maxc = std::max(d->syn_in, d->syn_out[d->n_syn_layers - 1]);
-    for (int l = 0; l < d->n_syn_layers; l++) maxc = std::max(maxc, d->syn_out[l]);
-    // conservative (as if nothing were fused) only when it is cheap; fused pairs never
-    // materialise their hidden layer, so bound by the widest NON-hidden layer when possible
-    int maxc_fused = std::max(d->syn_in, d->syn_out[d->n_syn_layers - 1]);
-    {
-        int in_ft = d->syn_in;
-        for (int l = 0; l < d->n_syn_layers; l++) {
-            const bool can = l + 1 < d->n_syn_layers && d->syn_k[l] == 1 && d->syn_k[l + 1] == 1 && !d->syn_res[l] &&
-                             !d->syn_res[l + 1] && in_ft <= 16 && d->syn_out[l + 1] <= 8;
-            if (can) {
-                maxc_fused = std::max(maxc_fused, d->syn_out[l + 1]);
-                in_ft = d->syn_out[l + 1];
-                l++;
-            } else {
-                maxc_fused = std::max(maxc_fused, d->syn_out[l]);
-                in_ft = d->syn_out[l];
-            }
-        }
-    }
-    (void)maxc;
-    const int C = d->syn_out[d->n_syn_layers - 1];
-    return al(plane * (size_t)(nl + 1) * 4) * 2 + al(plane * (size_t)maxc_fused * 4) * 2 + al(plane * (size_t)C * 4) + 4096;
-}
+size_t synthesis_scratch_bytes(const CcdCoolChicDesc *d) { return syn_scratch_plan(d).total + 4096; }
 
 }  // namespace
 

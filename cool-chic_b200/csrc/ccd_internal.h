@@ -106,6 +106,11 @@ int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, c
                        float *d_out, cudaStream_t st);
 int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st);
 int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st);
+// F.interpolate bilinear (mode 1) / bicubic (mode 2), align_corners=False; sy/sx = 0.5 (scale_factor 2) or in/out
+int ccd_resize_torch(const float *d_in, int c, int h, int w, float *d_out, int H, int W, int mode, float sy, float sx,
+                     cudaStream_t st);
+// samples [first, first+n) of the common-randomness generator (noise.py)
+int ccd_cr_noise(float *d_out, size_t first, size_t n, cudaStream_t st);
 int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, float *a, float *b, float *c,
                cudaStream_t st);
 

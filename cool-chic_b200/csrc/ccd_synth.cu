@@ -160,6 +160,89 @@ __global__ void k_resize_nearest(const float *__restrict__ in, int h, int w, flo
     out[((size_t)c * H + y) * W + x] = in[((size_t)c * h + yy) * w + xx];
 }
 
+// F.interpolate(mode = bilinear | bicubic, align_corners=False, antialias=False), same operation order as
+// oracle/ccoracle.c::resize_torch (PyTorch's separable CPU kernel): per axis src = fma(scale, dst + 0.5, -0.5),
+// taps clamped to the grid, A = -0.75 cubic coefficients; value = sum_i wy[i] * (sum_j wx[j] * v[i][j]) as fma chains.
+__device__ __forceinline__ float cubic_near(float x) {
+    const float a = __fsub_rn(__fmul_rn(1.25f, x), 2.25f);
+    return __fmaf_rn(__fmul_rn(a, x), x, 1.0f);
+}
+__device__ __forceinline__ float cubic_far(float x) {
+    const float a = __fadd_rn(__fmul_rn(-0.75f, x), 3.75f);
+    const float b = __fadd_rn(__fmul_rn(a, x), -6.0f);
+    return __fadd_rn(__fmul_rn(b, x), 3.0f);
+}
+template <int MODE>  // 1 bilinear (2 taps), 2 bicubic (4 taps)
+__device__ __forceinline__ void resize_taps(int n_in, int i, float scale, int (&idx)[4], float (&wt)[4]) {
+    float src = __fmaf_rn(scale, __fadd_rn((float)i, 0.5f), -0.5f);
+    if (MODE == 1 && src < 0.0f) src = 0.0f;
+    int i0 = (int)floorf(src);
+    if (i0 > n_in - 1) i0 = n_in - 1;
+    float lam = __fsub_rn(src, (float)i0);
+    lam = lam < 0.0f ? 0.0f : (lam > 1.0f ? 1.0f : lam);
+    if (MODE == 1) {
+        idx[0] = i0;
+        idx[1] = i0 + (i0 < n_in - 1 ? 1 : 0);
+        wt[0] = __fsub_rn(1.0f, lam);
+        wt[1] = lam;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) idx[j] = clampi(i0 + j - 1, 0, n_in - 1);
+        const float x2 = __fsub_rn(1.0f, lam);
+        wt[0] = cubic_far(__fadd_rn(lam, 1.0f));
+        wt[1] = cubic_near(lam);
+        wt[2] = cubic_near(x2);
+        wt[3] = cubic_far(__fadd_rn(x2, 1.0f));
+    }
+}
+template <int MODE>
+__global__ void k_resize_torch(const float *__restrict__ in, int h, int w, float *__restrict__ out, int H, int W,
+                               float sy, float sx) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c = blockIdx.z;
+    if (x >= W || y >= H) return;
+    constexpr int N = MODE == 1 ? 2 : 4;
+    int iy[4], ix[4];
+    float wy[4], wx[4];
+    resize_taps<MODE>(h, y, sy, iy, wy);
+    resize_taps<MODE>(w, x, sx, ix, wx);
+    const float *p = in + (size_t)c * h * w;
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const float *row = p + (size_t)iy[i] * w;
+        float r = __fmul_rn(wx[0], __ldg(row + ix[0]));
+#pragma unroll
+        for (int j = 1; j < N; j++) r = __fmaf_rn(wx[j], __ldg(row + ix[j]), r);
+        acc = (i == 0) ? __fmul_rn(wy[0], r) : __fmaf_rn(wy[i], r, acc);
+    }
+    out[((size_t)c * H + y) * W + x] = acc;
+}
+
+// Common randomness (core/noise.py:18-55): sample k of the Park-Miller sequence, Box-Muller in f64.
+// seed_j = a^j * seed_0 mod m is evaluated directly (square-and-multiply) instead of serially.
+__device__ __forceinline__ uint64_t lcg_pow(uint64_t e) {
+    const uint64_t m = 2147483647ULL;
+    uint64_t r = 1, b = 16807ULL;
+    while (e) {
+        if (e & 1) r = (r * b) % m;
+        b = (b * b) % m;
+        e >>= 1;
+    }
+    return r;
+}
+__global__ void k_cr_noise(float *__restrict__ out, size_t first, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t m = 2147483647ULL;
+    const size_t k = first + i;
+    const uint64_t s1 = (lcg_pow(2 * k + 1) * 18101995ULL) % m;
+    const uint64_t s2 = (s1 * 16807ULL) % m;
+    const double u1 = (double)s1 / (double)m, u2 = (double)s2 / (double)m;
+    out[i] = (float)(sqrt(-2 * log(u1)) * cos(2 * 3.14159265359 * u2));
+}
+
 __device__ __forceinline__ float quant(float v, float M) { return __fdiv_rn(rintf(__fmul_rn(M, v)), M); }
 __device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 
@@ -243,6 +326,22 @@ int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st) {
 int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st) {
     k_resize_nearest<<<grid2(W, H, c), kBlock2, 0, st>>>(d_in, h, w, d_out, H, W, (float)h / (float)H,
                                                          (float)w / (float)W);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+int ccd_resize_torch(const float *d_in, int c, int h, int w, float *d_out, int H, int W, int mode, float sy, float sx,
+                     cudaStream_t st) {
+    if (mode == 1)
+        k_resize_torch<1><<<grid2(W, H, c), kBlock2, 0, st>>>(d_in, h, w, d_out, H, W, sy, sx);
+    else
+        k_resize_torch<2><<<grid2(W, H, c), kBlock2, 0, st>>>(d_in, h, w, d_out, H, W, sy, sx);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+int ccd_cr_noise(float *d_out, size_t first, size_t n, cudaStream_t st) {
+    k_cr_noise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_out, first, n);
     g_ccd_launches++;
     return (int)cudaGetLastError();
 }

@@ -131,6 +131,11 @@ def adapt_nn(src_d: CcdCoolChicDesc, src_ints: np.ndarray, dst_d: CcdCoolChicDes
             else:
                 cand = np.zeros(shape, dtype=np.int64)
             dst[key][name] = _fit(cand, shape) if cand.shape != tuple(shape) else cand.copy()
+    if dst_d.common_randomness and not src_d.common_randomness:
+        # the noise half of the synthesis input gets (attenuated) copies of the latent half's weights
+        w0 = dst["synthesis.weight"]["l0"]
+        half = dst_d.syn_in // 2
+        w0[:, half:] = w0[:, :half] // 3 + 1
     ints, _ = join_nn(dst_d, dst)
     return ints
 
@@ -253,14 +258,17 @@ def make_coolchic(ctx, seed_stream: SeedStream, img_size, latent_resolution=(0, 
 
 
 def make_image_stream(ctx, seed_stream: SeedStream, height: int, width: int, frame_data_type: str = "rgb",
-                      bitdepth: int = 8, latent_resolution=(0, 6), hyperlatent_resolution=None, seed: int = 0) -> bytes:
-    """A complete single-frame (intra) bitstream."""
+                      bitdepth: int = 8, latent_resolution=(0, 6), hyperlatent_resolution=None, seed: int = 0,
+                      final_upsampling_type: Optional[str] = None, overrides: Optional[dict] = None) -> bytes:
+    """A complete single-frame (intra) bitstream.  ``overrides`` sets Cool-chic header fields, e.g.
+    ``{"flag_common_randomness": 1}``; ``final_upsampling_type`` matters when latent_resolution[0] > 0."""
     v = VideoHeader()
     v.set_header(1, [0], [])
     f = FrameHeader()
     f._values.update(display_index=0, frame_type="I", frame_data_type=frame_data_type, bitdepth=bitdepth,
                      index_references=[], global_flow=[])
-    cc, _, _ = make_coolchic(ctx, seed_stream, (height, width), latent_resolution, hyperlatent_resolution, seed)
+    cc, _, _ = make_coolchic(ctx, seed_stream, (height, width), latent_resolution, hyperlatent_resolution, seed,
+                             final_upsampling_type, overrides)
     return v.to_bytes() + f.to_bytes() + cc
 
 

@@ -898,12 +898,144 @@ static void syn_conv(const float *in, int cin, int h, int w, const float *wt, co
             }
 }
 
+/* ---- F.interpolate(mode = "bilinear" | "bicubic", align_corners=False, antialias=False) ------------
+ * Restated from PyTorch's CPU kernel (aten/native/cpu/UpSampleKernel.cpp, generic separable path):
+ *   src = fma(scale, dst + 0.5, -0.5) in fp32 (bilinear: max(src, 0)); i0 = min(floor(src), in-1);
+ *   lambda = clamp(src - i0, 0, 1); taps clamped to the grid; A = -0.75 cubic coefficients;
+ *   value = sum_i wy[i] * (sum_j wx[j] * v[i][j]), products accumulated by an fma chain.
+ * scale = 1/scale_factor when a scale factor was given (fixed_upsampling, upsampling.py:586: 0.5),
+ * else (float)in / out (component/coolchic.py:187-189).  mode: 1 bilinear, 2 bicubic. */
+static float cubic_near(float x);
+static float cubic_far(float x);
+typedef struct { int idx[4]; float w[4]; } Tap;
+static void resize_taps(int in, int out, float scale, int mode, Tap *t) {
+    for (int i = 0; i < out; i++) {
+        float src = fmaf(scale, (float)i + 0.5f, -0.5f); /* contracted in PyTorch's build */
+        if (mode == 1 && src < 0.0f) src = 0.0f;
+        int i0 = (int)floorf(src);
+        if (i0 > in - 1) i0 = in - 1;
+        float lam = src - (float)i0;
+        lam = lam < 0.0f ? 0.0f : (lam > 1.0f ? 1.0f : lam);
+        if (mode == 1) {
+            t[i].idx[0] = i0;
+            t[i].idx[1] = i0 + (i0 < in - 1 ? 1 : 0);
+            t[i].w[0] = 1.0f - lam;
+            t[i].w[1] = lam;
+        } else {
+            for (int j = 0; j < 4; j++) t[i].idx[j] = clampi(i0 + j - 1, 0, in - 1);
+            t[i].w[0] = cubic_far(lam + 1.0f);
+            t[i].w[1] = cubic_near(lam);
+            float x2 = 1.0f - lam;
+            t[i].w[2] = cubic_near(x2);
+            t[i].w[3] = cubic_far(x2 + 1.0f);
+        }
+    }
+}
+static int resize_torch(const float *in, int c, int h, int w, float *out, int H, int W, int ldH, int ldW, int mode,
+                        float sy, float sx) {
+    /* writes the top-left H x W (crop) of the resized planes into out[c][ldH][ldW] */
+    Tap *ty = (Tap *)malloc(sizeof(Tap) * (size_t)(H + W));
+    if (!ty) return CCO_ERR_NOMEM;
+    Tap *tx = ty + H;
+    resize_taps(h, H, sy, mode, ty);
+    resize_taps(w, W, sx, mode, tx);
+    const int n = mode == 1 ? 2 : 4;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int ch = 0; ch < c; ch++)
+        for (int y = 0; y < H; y++) {
+            const float *p = in + (size_t)ch * h * w;
+            for (int x = 0; x < W; x++) {
+                float acc = 0.0f;
+                for (int i = 0; i < n; i++) {
+                    const float *row = p + (size_t)ty[y].idx[i] * w;
+                    float r = tx[x].w[0] * row[tx[x].idx[0]];
+                    for (int j = 1; j < n; j++) r = fmaf(tx[x].w[j], row[tx[x].idx[j]], r);
+                    acc = (i == 0) ? ty[y].w[0] * r : fmaf(ty[y].w[i], r, acc);
+                }
+                out[((size_t)ch * ldH + y) * ldW + x] = acc;
+            }
+        }
+    free(ty);
+    return CCO_OK;
+}
+int cco_resize(const float *in, int c, int h, int w, float *out, int H, int W, int mode, int scale_factor_2) {
+    if (mode != 1 && mode != 2) return CCO_ERR_ARG;
+    float sy = scale_factor_2 ? 0.5f : (float)h / (float)H, sx = scale_factor_2 ? 0.5f : (float)w / (float)W;
+    return resize_torch(in, c, h, w, out, H, W, H, W, mode, sy, sx);
+}
+
+/* ---- common randomness (--tune=wasserstein): component/core/noise.py:18-55 ------------------------
+ * Park-Miller LCG (a = 7^5, m = 2^31 - 1, seed 18101995), two draws per sample, Box-Muller in
+ * double precision with pi = 3.14159265359, rounded to fp32; one grid per latent resolution
+ * (core/coolchic.py:187-191: ceil(img / 2^i)), finest first; fixed_upsampling(bicubic)
+ * (upsampling.py:556-595) and a final bicubic interpolate to the image size
+ * (bitstream/component/coolchic.py:180-183).  out: [n][H][W], n = latent_res_hi - latent_res_lo + 1. */
+int cco_cr_noise(const CcoDesc *d, float *out) {
+    const int n = d->latent_res_hi - d->latent_res_lo + 1;
+    if (n < 1 || n > CCO_MAX_GRIDS) return CCO_ERR_ARG;
+    const int H = d->img_h, W = d->img_w;
+    int gh[CCO_MAX_GRIDS], gw[CCO_MAX_GRIDS];
+    float *g[CCO_MAX_GRIDS];
+    uint64_t seed = 18101995ULL;
+    const uint64_t a = 16807ULL, m = 2147483647ULL;
+    const double pi = 3.14159265359;
+    for (int i = 0; i < n; i++) g[i] = NULL;
+    int rc = CCO_OK;
+    for (int i = 0; i < n && rc == CCO_OK; i++) {
+        const int sh = d->latent_res_lo + i;
+        gh[i] = (int)ceil((double)H / (double)(1LL << sh));
+        gw[i] = (int)ceil((double)W / (double)(1LL << sh));
+        size_t cnt = (size_t)gh[i] * gw[i];
+        g[i] = (float *)malloc(cnt * 4 + 16);
+        if (!g[i]) { rc = CCO_ERR_NOMEM; break; }
+        for (size_t k = 0; k < cnt; k++) {
+            seed = (a * seed) % m;
+            double u1 = (double)seed / (double)m;
+            seed = (a * seed) % m;
+            double u2 = (double)seed / (double)m;
+            g[i][k] = (float)(sqrt(-2 * log(u1)) * cos(2 * pi * u2));
+        }
+    }
+    /* cascade, coarsest first; cur holds cc planes of size ch x cw */
+    float *cur = NULL, *nxt = NULL;
+    int ch = 0, cw = 0, cc = 0;
+    if (rc == CCO_OK) {
+        size_t plane0 = (size_t)gh[0] * gw[0];
+        cur = (float *)malloc(plane0 * (size_t)n * 4 + 16);
+        nxt = (float *)malloc(plane0 * (size_t)n * 4 + 16);
+        if (!cur || !nxt) rc = CCO_ERR_NOMEM;
+    }
+    if (rc == CCO_OK) {
+        ch = gh[n - 1]; cw = gw[n - 1]; cc = 1;
+        memcpy(cur, g[n - 1], (size_t)ch * cw * 4);
+        for (int i = n - 2; i >= 0 && rc == CCO_OK; i--) {
+            const int th = gh[i], tw = gw[i];
+            memcpy(nxt, g[i], (size_t)th * tw * 4);
+            if (th != ch || tw != cw) {
+                /* interpolate(scale_factor=2) gives 2ch x 2cw >= th x tw, cropped */
+                if (th > 2 * ch || tw > 2 * cw) { rc = CCO_ERR_ARG; break; }
+                rc = resize_torch(cur, cc, ch, cw, nxt + (size_t)th * tw, th, tw, th, tw, 2, 0.5f, 0.5f);
+            } else {
+                memcpy(nxt + (size_t)th * tw, cur, (size_t)cc * ch * cw * 4);
+            }
+            float *t = cur; cur = nxt; nxt = t;
+            ch = th; cw = tw; cc++;
+        }
+    }
+    if (rc == CCO_OK) {
+        if (ch == H && cw == W) memcpy(out, cur, (size_t)n * H * W * 4); /* bicubic at scale 1 = identity */
+        else rc = resize_torch(cur, n, ch, cw, out, H, W, H, W, 2, (float)ch / (float)H, (float)cw / (float)W);
+    }
+    for (int i = 0; i < n; i++) free(g[i]);
+    free(cur); free(nxt);
+    return rc;
+}
+
 int cco_synthesize(const CcoDesc *d, const int64_t *nn, const int8_t *latents, float *out,
                    float *dense_opt) {
     NNLayout L;
     int rc = nn_layout(d, &L);
     if (rc) return rc;
-    if (d->common_randomness) return CCO_ERR_UNSUPPORTED;
     if (d->ups_k < 4 || (d->ups_k & 1) || !(d->ups_pre_k & 1) || d->ups_k > 15 || d->ups_pre_k > 15)
         return CCO_ERR_ARG;
     int64_t offs[CCO_MAX_GRIDS];
@@ -912,13 +1044,16 @@ int cco_synthesize(const CcoDesc *d, const int64_t *nn, const int8_t *latents, f
     int gl[CCO_MAX_GRIDS], nl = 0;
     for (int g = 0; g < d->n_grids; g++)
         if (!d->grid_is_hyper[g]) gl[nl++] = g;
-    if (nl != d->syn_in) return CCO_ERR_ARG;
+    const int cr = d->common_randomness != 0;
+    if (nl * (cr ? 2 : 1) != d->syn_in) return CCO_ERR_ARG;
     float qs_uw = ldexpf(1.0f, d->qshift[4]);
     float qs_sw = ldexpf(1.0f, d->qshift[6]), qs_sb = ldexpf(1.0f, d->qshift[7]);
     int h0 = d->grid_h[gl[0]], w0 = d->grid_w[gl[0]];
     size_t plane0 = (size_t)h0 * w0;
-    float *cur = (float *)malloc(plane0 * (size_t)(nl + 1) * 4 + 16);
-    float *nxt = (float *)malloc(plane0 * (size_t)(nl + 1) * 4 + 16);
+    if (cr && (h0 != d->img_h || w0 != d->img_w || nl != d->latent_res_hi - d->latent_res_lo + 1))
+        return CCO_ERR_ARG; /* the reference concatenates noise at image size with the dense latent */
+    float *cur = (float *)malloc(plane0 * (size_t)(2 * nl + 1) * 4 + 16);
+    float *nxt = (float *)malloc(plane0 * (size_t)(2 * nl + 1) * 4 + 16);
     if (!cur || !nxt) {
         free(cur);
         free(nxt);
@@ -956,7 +1091,16 @@ int cco_synthesize(const CcoDesc *d, const int64_t *nn, const int8_t *latents, f
         cw = tw;
         cc++;
     }
-    if (dense_opt) memcpy(dense_opt, cur, plane0 * (size_t)nl * 4);
+    if (cr) {
+        /* bitstream/component/coolchic.py:179-183: noise channels appended to the dense latent */
+        rc = cco_cr_noise(d, cur + plane0 * (size_t)nl);
+        if (rc) {
+            free(cur);
+            free(nxt);
+            return rc;
+        }
+    }
+    if (dense_opt) memcpy(dense_opt, cur, plane0 * (size_t)d->syn_in * 4);
     /* ---- synthesis */
     int C = L.syn_c_out;
     int maxc = d->syn_in;
@@ -1020,7 +1164,9 @@ int cco_synthesize(const CcoDesc *d, const int64_t *nn, const int8_t *latents, f
                 }
             }
     } else {
-        rc = CCO_ERR_UNSUPPORTED;
+        /* size is given -> scale = in / out; output is exactly img size, nothing to crop */
+        rc = resize_torch(b, C, h0, w0, out, H, W, H, W, d->final_ups == 1 ? 1 : 2, (float)h0 / (float)H,
+                          (float)w0 / (float)W);
     }
     free(a); free(b); free(stab); free(wbuf); free(cur); free(nxt);
     return rc;

@@ -106,6 +106,13 @@ int64_t cco_sample_latents(const CcoDesc *d, const int64_t *nn, uint64_t seed, i
 int cco_synthesize(const CcoDesc *d, const int64_t *nn, const int8_t *latents, float *out,
                    float *dense_opt);
 
+/* F.interpolate(align_corners=False) of [c][h][w] to [c][H][W]; mode 1 bilinear, 2 bicubic;
+ * scale_factor_2: the call gave scale_factor=2.0 (scale 0.5) instead of a size. */
+int cco_resize(const float *in, int c, int h, int w, float *out, int H, int W, int mode,
+               int scale_factor_2);
+/* common-randomness synthesis input (noise.py + fixed_upsampling bicubic): out [n][img_h][img_w] */
+int cco_cr_noise(const CcoDesc *d, float *out);
+
 /* decode_frame tail for I frames (bitstream/decode.py:191-206): round -> (444->420 avg pool)
  * -> clamp -> round.  data_type 0 rgb, 1 yuv420, 2 yuv444.  in: [3][H][W]; out planes:
  * rgb/444: out_a [3][H][W];  420: out_a = y [H][W], out_b = u, out_c = v [H/2][W/2]. */

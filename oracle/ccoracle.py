@@ -56,6 +56,10 @@ def lib():
                                         ctypes.c_int, vp]
         L.cco_laplace_domain.restype = None
         L.cco_laplace_domain.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp]
+        L.cco_resize.restype = ctypes.c_int
+        L.cco_resize.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp] + [ctypes.c_int] * 4
+        L.cco_cr_noise.restype = ctypes.c_int
+        L.cco_cr_noise.argtypes = [vp, vp]
         L.cco_laplace_left.restype = ctypes.c_uint32
         L.cco_laplace_left.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float]
         _lib = L
@@ -192,4 +196,23 @@ def inter_predict(residue, motion, ref0, ref1, global_flow, warp_filter_size):
     out = np.zeros((3, h, w), dtype=np.float32)
     _chk(lib().cco_inter_predict(_p(residue), _p(motion), _p(ref0), _p(ref1) if is_b else None, h, w, int(is_b),
                                  _p(gf), int(warp_filter_size), _p(out)), "inter_predict")
+    return out
+
+
+def resize(x: np.ndarray, size, mode: str, scale_factor_2: bool = False) -> np.ndarray:
+    """F.interpolate(x[None], size | scale_factor=2, mode, align_corners=False)[0] for [C,h,w] fp32."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    c, h, w = x.shape
+    H, W = size
+    out = np.zeros((c, H, W), dtype=np.float32)
+    _chk(lib().cco_resize(_p(x), c, h, w, _p(out), H, W, {"bilinear": 1, "bicubic": 2}[mode], int(scale_factor_2)),
+         "resize")
+    return out
+
+
+def cr_noise(desc) -> np.ndarray:
+    """Common-randomness channels of the synthesis input: [n_latent_resolutions, img_h, img_w]."""
+    n = desc.latent_res_hi - desc.latent_res_lo + 1
+    out = np.zeros((n, desc.img_h, desc.img_w), dtype=np.float32)
+    _chk(lib().cco_cr_noise(ctypes.byref(desc), _p(out)), "cr_noise")
     return out

@@ -340,3 +340,50 @@ def test_gop_1080p_yuv420_properties(ctx, seed_stream):
             lv = t * 255
             assert float((lv - torch.round(lv)).abs().max()) < 1e-3 and float(t.min()) >= 0 and float(t.max()) <= 1
     assert rest == b""
+
+
+# ----------------------------------------------------------------------------------------------
+# optional branches of the synthesis input / output
+@pytest.mark.parametrize("name", ["img_48x72_rgb_common_randomness", "img_50x70_rgb_final_bicubic",
+                                  "img_44x60_yuv420_final_bilinear"])
+def test_optional_synthesis_branches(ctx, oracle, name):
+    """Common randomness and bilinear / bicubic final resize on the device: raw synthesis output vs the
+    oracle (tolerance: device f64 log / cos are not glibc's; everything else is the same fp32 sequence),
+    decoded image vs the UNMODIFIED reference's (oracle/gen_golden_modes.py)."""
+    from coolchic_b200 import synth
+    from coolchic_b200._desc import desc_from_header
+    from coolchic_b200.bitstream.decode import decode_video
+
+    path = os.path.join(GOLDEN, name + ".cool")
+    data = open(path, "rb").read()
+    _, f, c, nn_bytes, payload = synth.parse_single_image(data)
+    desc = desc_from_header(c)
+    raw = ctx.decode_coolchic(desc, nn_bytes, payload).cpu().numpy()[0]
+    nn = oracle.decode_nn(desc, nn_bytes)
+    lat, _ = oracle.decode_latents(desc, nn, payload)
+    want = oracle.synthesize(desc, nn, lat)
+    assert np.abs(raw - want).max() <= 1e-6
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fd = decode_video(path, None)["0"]
+    for k in gold.files:
+        got = np.round((fd.data[k][0, 0] if k in "yuv" else fd.data[0]).numpy() * 255).astype(np.int32)
+        assert np.abs(got - gold[k].astype(np.int32)).max() <= 1
+        assert (got != gold[k]).sum() <= 2
+
+
+def test_common_randomness_1080p_properties(ctx, seed_stream):
+    """Full-size common-randomness stream: decodes, deterministic, and the noise half of the input matters."""
+    from coolchic_b200 import synth
+    from coolchic_b200._desc import desc_from_header
+
+    data = synth.make_image_stream(ctx, seed_stream, 1080, 1920, "rgb", 8, (0, 6), None, seed=1,
+                                   overrides={"flag_common_randomness": 1})
+    _, f, c, nn_bytes, payload = synth.parse_single_image(data)
+    desc = desc_from_header(c)
+    a = ctx.decode_coolchic(desc, nn_bytes, payload)
+    b = ctx.decode_coolchic(desc, nn_bytes, payload)
+    assert a.shape == (1, 3, 1080, 1920) and bool((a == b).all()) and bool(a.isfinite().all())
+    plain = synth.make_image_stream(ctx, seed_stream, 1080, 1920, "rgb", 8, (0, 6), None, seed=1)
+    _, _, c2, nn2, pay2 = synth.parse_single_image(plain)
+    p = ctx.decode_coolchic(desc_from_header(c2), nn2, pay2)
+    assert float((a - p).abs().mean()) > 1e-3
