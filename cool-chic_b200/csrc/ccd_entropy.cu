@@ -135,6 +135,9 @@ __device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
     asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ void sts_v2(uint32_t a, uint2 v) {
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;
     asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -168,7 +171,8 @@ struct SmemLayout {
     unsigned char *ifce;   // IFCE blob of the current grid
     uint32_t meta;         // shared address: uint4 [ring]
     uint32_t win;          // shared address: u32 [ring][32]: left(s_lo + t), t = 0..31 (mode at t = 15)
-    uint32_t res;          // shared address: u32 [ring]: decoded result of each symbol (coder -> helper)
+    uint32_t hot;          // shared address: uint4 [ring]: left(M), left(M+1)-left(M), left(M-1), left(M+2), M = mode
+    uint32_t res;          // shared address: u32 [ring]: result word of each symbol that is NOT the mode (coder -> helper)
     uint32_t bc;           // shared address: 16 B broadcast line of the coder warp (new D, R)
     uint32_t rows;         // shared address: int8 [rows][64]
 };
@@ -195,6 +199,8 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int r
     p += (size_t)ring * 16;
     L.win = base_a + (uint32_t)p;
     p += (size_t)ring * CCD_WIN * 4;
+    L.hot = base_a + (uint32_t)p;
+    p += (size_t)ring * 16;
     L.res = base_a + (uint32_t)p;
     p += (size_t)ring * 4;
     L.rows = base_a + (uint32_t)p;
@@ -508,8 +514,18 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
             const int s0 = s_lo + 8 * member;
             sts_v4(wdst + 32u * member, make_uint4(fix_left(va.x, s0), fix_left(va.y, s0 + 1), fix_left(va.z, s0 + 2),
                                                    fix_left(va.w, s0 + 3)));
-            sts_v4(wdst + 32u * member + 16u, make_uint4(fix_left(vb.x, s0 + 4), fix_left(vb.y, s0 + 5),
-                                                         fix_left(vb.z, s0 + 6), fix_left(vb.w, s0 + 7)));
+            const uint4 fb = make_uint4(fix_left(vb.x, s0 + 4), fix_left(vb.y, s0 + 5), fix_left(vb.z, s0 + 6),
+                                        fix_left(vb.w, s0 + 7));
+            sts_v4(wdst + 32u * member + 16u, fb);
+            // hot entry (the coder's steady state reads nothing else): window entries 13 .. 16
+            static_assert(CCD_WIN_HALF == 14, "hot entry layout");
+            const uint32_t hdst = sm.hot + slot * 16u;
+            if (member == 1) {
+                sts_v2(hdst, make_uint2(fb.z, fb.w - fb.z));
+                sts_u32(hdst + 8u, fb.y);
+            } else if (member == 2) {
+                sts_u32(hdst + 12u, fix_left(va.x, s0));
+            }
         }
         __threadfence_block();
         __syncwarp();
@@ -522,6 +538,11 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
             for (int c = 0; c < 8; c++)
                 sts_v4(wdst + 16u * c, make_uint4(fix_left(v[c].x, s_lo + 4 * c), fix_left(v[c].y, s_lo + 4 * c + 1),
                                                   fix_left(v[c].z, s_lo + 4 * c + 2), fix_left(v[c].w, s_lo + 4 * c + 3)));
+            {
+                const uint32_t l13 = fix_left(v[3].y, s_lo + 13), l14 = fix_left(v[3].z, s_lo + 14);
+                const uint32_t l15 = fix_left(v[3].w, s_lo + 15), l16 = fix_left(v[4].x, s_lo + 16);
+                sts_v4(sm.hot + slot * 16u, make_uint4(l14, l15 - l14, l13, l16));
+            }
             __threadfence_block();
         }
     }
@@ -657,6 +678,7 @@ struct DecState {
     uint32_t wcur, wnxt;  // lane l holds word (32*chunk + l) of the current / next chunk
     uint32_t wnext;       // word[wpos], broadcast
     uint32_t slow;
+    uint32_t n_far;       // symbols that were not the mode (instrumented build)
     int err;
 };
 
@@ -669,70 +691,46 @@ __device__ __noinline__ void dec_advance_word(const SLoc &S, DecState &c, int la
     c.wnext = __shfl_sync(0xffffffffu, c.wcur, (int)(c.wpos & 31));
 }
 
-// result word of symbol j: [31] value is the symbol itself (else the window index t), [30:8] tag, [7:0] value
+// result word of a symbol j that is not the mode: [31] value is the symbol itself (else the window index t),
+// [30] valid (an all-zero word never matches), [29:8] tag = (j + 1) mod 2^22, [7:0] value
+__device__ __forceinline__ uint32_t res_tag(uint32_t j) { return 0x40000000u | (((j + 1u) & 0x3fffffu) << 8); }
 __device__ __forceinline__ uint32_t res_word(uint32_t j, uint32_t value, bool is_symbol) {
-    return ((uint32_t)is_symbol << 31) | (((j + 1u) & 0x7fffffu) << 8) | (value & 0xffu);
+    return ((uint32_t)is_symbol << 31) | res_tag(j) | (value & 0xffu);
 }
 
+// Out-of-line parts of the coder take and return everything BY VALUE (registers), never through a
+// reference into the kernel's local-memory state.
 struct FarOut {
     uint64_t lo, hi;
     uint32_t rw;
+    uint32_t flags;  // 2: outside the window (exact search), 4: desynchronised
 };
 
-// Symbol is not the mode: neighbours of the mode first, then the rest of the 32-entry window,
-// then the exact f64 model (warp-cooperative).  Out of line: keeps the hot loop small.
-__device__ __noinline__ FarOut coder_far(const SmemLayout &sm, const float *__restrict__ scale_tab, uint32_t ring_mask,
-                                         int lane, uint32_t j, uint64_t scale, uint64_t D, uint32_t *slow, int *err) {
+// Symbol is neither the mode nor one of its two neighbours: the whole 32-entry window at once (lane per
+// entry), then the exact f64 model (warp-cooperative).
+__device__ __noinline__ FarOut coder_far(uint32_t wrow, uint32_t meta_slot, const float *__restrict__ scale_tab, int lane,
+                                         uint32_t j, uint64_t scale, uint64_t D) {
     FarOut o;
-    const uint32_t wrow = sm.win + (j & ring_mask) * (CCD_WIN * 4);
-    // The mode sits at t = M.  Its neighbours t = M-2 .. M+4 are fetched with two LDS.128 issued
-    // together and tested with ALU ops only; farther symbols walk the window one LDS at a time.
-    constexpr int M = CCD_WIN_HALF;
-    const uint4 A = lds_v4(wrow + 4u * (M - 2));  // left(M-2), left(M-1), left(M), left(M+1)
-    const uint4 B = lds_v4(wrow + 4u * (M + 2));  // left(M+2) .. left(M+5)
-    const uint64_t PM = scale * A.z;
-    if (D < PM) {
-        const uint64_t P1 = scale * A.y;
-        if (P1 <= D) { o.lo = P1; o.hi = PM; o.rw = res_word(j, M - 1, false); return o; }
-        const uint64_t P2 = scale * A.x;
-        if (P2 <= D) { o.lo = P2; o.hi = P1; o.rw = res_word(j, M - 2, false); return o; }
-        uint64_t hi = P2;
-        for (int t = M - 3; t >= 0; t--) {
-            const uint64_t lo = scale * lds_u32(wrow + 4u * (uint32_t)t);
-            if (lo <= D) {
-                o.lo = lo; o.hi = hi; o.rw = res_word(j, (uint32_t)t, false);
-                return o;
-            }
-            hi = lo;
-        }
-    } else {
-        const uint64_t Q1 = scale * A.w;  // P[M+1] <= D here (the mode was rejected)
-        const uint64_t Q2 = scale * B.x;
-        if (D < Q2) { o.lo = Q1; o.hi = Q2; o.rw = res_word(j, M + 1, false); return o; }
-        const uint64_t Q3 = scale * B.y;
-        if (D < Q3) { o.lo = Q2; o.hi = Q3; o.rw = res_word(j, M + 2, false); return o; }
-        const uint64_t Q4 = scale * B.z;
-        if (D < Q4) { o.lo = Q3; o.hi = Q4; o.rw = res_word(j, M + 3, false); return o; }
-        const uint64_t Q5 = scale * B.w;
-        if (D < Q5) { o.lo = Q4; o.hi = Q5; o.rw = res_word(j, M + 4, false); return o; }
-        uint64_t lo = Q5;
-        for (int t = M + 5; t < 31; t++) {
-            const uint64_t hi = scale * lds_u32(wrow + 4u * (uint32_t)(t + 1));
-            if (D < hi) {
-                o.lo = lo; o.hi = hi; o.rw = res_word(j, (uint32_t)t, false);
-                return o;
-            }
-            lo = hi;
-        }
+    o.flags = 0;
+    // lane t evaluates window entry t: one conflict-free LDS, one product, one vote -- the cost does not
+    // depend on how far from the mode the symbol is (wide distributions of the coarse grids)
+    const uint32_t Lt = lds_u32(wrow + 4u * (uint32_t)lane);
+    const uint32_t b = __ballot_sync(0xffffffffu, scale * Lt <= D);  // lefts are non-decreasing: bits 0..t
+    if (b != 0u && b != 0xffffffffu) {
+        const int t = 31 - __clz((int)b);
+        o.lo = scale * (uint64_t)__shfl_sync(0xffffffffu, Lt, t);
+        o.hi = scale * (uint64_t)__shfl_sync(0xffffffffu, Lt, t + 1);
+        o.rw = res_word(j, (uint32_t)t, false);
+        return o;
     }
     // outside the window, or corrupt stream
-    (*slow)++;
+    o.flags = 2;
     uint64_t q = D / scale;
     if (q >= (1ull << 24)) {
-        *err = CCD_ERR_DESYNC;
+        o.flags |= 4;
         q = (1ull << 24) - 1;
     }
-    const uint4 m = lds_v4(sm.meta + (j & ring_mask) * 16u);
+    const uint4 m = lds_v4(meta_slot);
     const uint4 r = slow_search((uint32_t)q, (int)(m.z & 0xffffu), (int)(m.z >> 16), scale_tab, lane);
     o.lo = scale * (uint64_t)__shfl_sync(0xffffffffu, r.x, (int)r.z);
     o.hi = scale * (uint64_t)__shfl_sync(0xffffffffu, r.y, (int)r.z);
@@ -740,52 +738,120 @@ __device__ __noinline__ FarOut coder_far(const SmemLayout &sm, const float *__re
     return o;
 }
 
-// One symbol of the recursion, executed IDENTICALLY by every lane of the coder warp: no vote,
-// no shuffle, no shared-memory round trip on the serial chain -- only 64-bit integer ALU ops.
-// LM = (left(mode), left(mode + 1)): the most probable symbol is tested speculatively.
-__device__ __forceinline__ void coder_step(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
-                                           uint32_t ring_mask, int lane, uint32_t j, uint2 LM, uint64_t &D,
-                                           uint64_t &R, uint32_t &wnext, DecState &c, ProfCounters &pc) {
+// Everything that is not "the mode, no renormalisation": the two neighbours of the mode from the hot
+// entry, any other symbol through coder_far, the result word for the helper, the renormalisation.
+// Out of line (about one symbol in seven): the steady loop stays ~20 instructions per symbol.
+struct SlowOut {
+    uint32_t d_lo, d_hi, r_lo, r_hi;  // (D, R) after the symbol
+    uint32_t flags;                   // 1: consumed the next word, 2 / 4: see FarOut, 8: not the mode
+};
+__device__ __noinline__ SlowOut coder_slow(uint32_t res_a, uint32_t win_a, uint32_t meta_a,
+                                           const float *__restrict__ scale_tab, uint32_t ring_mask, int lane, uint32_t j,
+                                           uint4 h, uint64_t D, uint64_t R, uint32_t wnext) {
+    constexpr uint32_t M = CCD_WIN_HALF;
     const uint64_t scale = R >> 24;
-    uint64_t lo = scale * LM.x, hi = scale * LM.y;
-    uint32_t rw = res_word(j, (uint32_t)CCD_WIN_HALF, false);
-    if (!((lo <= D) && (D < hi))) {
-        PROF_T(tf);
-        const FarOut f = coder_far(sm, scale_tab, ring_mask, lane, j, scale, D, &c.slow, &c.err);
-#ifdef CCD_PROFILE
-        pc.seg[1]++;
-        if (f.rw == 0xffffffffu) pc.seg[5]++;
-        pc.seg[2] += clock64() - tf;
-#endif
-        lo = f.lo;
-        hi = f.hi;
-        rw = f.rw;
+    uint64_t lo = scale * h.x;
+    uint64_t Rn = scale * h.y;
+    uint64_t Dn = D - lo;
+    uint32_t flags = 0;
+    if (!(Dn < Rn)) {
+        flags = 8;
+        const uint64_t hiM = lo + Rn;  // = scale * left(M + 1)
+        const uint32_t slot = j & ring_mask;
+        uint64_t hi = 0;
+        uint32_t rw = 0;
+        bool found = false;
+        if (D < lo) {
+            const uint64_t p1 = scale * h.z;
+            if (p1 <= D) {
+                hi = lo;
+                lo = p1;
+                rw = res_word(j, M - 1u, false);
+                found = true;
+            }
+        } else {
+            const uint64_t q2 = scale * h.w;
+            if (D < q2) {
+                lo = hiM;
+                hi = q2;
+                rw = res_word(j, M + 1u, false);
+                found = true;
+            }
+        }
+        if (!found) {
+            const FarOut f = coder_far(win_a + slot * (CCD_WIN * 4), meta_a + slot * 16u, scale_tab, lane, j, scale, D);
+            lo = f.lo;
+            hi = f.hi;
+            rw = f.rw;
+            flags |= f.flags;
+        }
+        Dn = D - lo;
+        Rn = hi - lo;
+        // shared-memory stores of one warp are performed in program order: this word is visible before the
+        // `done` store that follows it
+        if (lane == 0) sts_u32(res_a + slot * 4u, rw);
     }
-    D -= lo;
-    R = hi - lo;
-    asm volatile(
-        "{\n .reg .pred p;\n setp.eq.s32 p, %0, 0;\n @p st.volatile.shared.u32 [%1], %2;\n}\n" ::"r"(lane),
-        "r"(sm.res + (j & ring_mask) * 4u), "r"(rw)
-        : "memory");
-    if ((R >> 32) == 0) {  // at most one renormalisation per symbol
-        R <<= 32;
-        D = (D << 32) | wnext;
-        dec_advance_word(S, c, lane);
-        wnext = c.wnext;
+    if ((Rn >> 32) == 0) {  // at most one renormalisation per symbol
+        Rn <<= 32;
+        Dn = (Dn << 32) | wnext;
+        flags |= 1;
     }
+    SlowOut o;
+    o.d_lo = (uint32_t)Dn;
+    o.d_hi = (uint32_t)(Dn >> 32);
+    o.r_lo = (uint32_t)Rn;
+    o.r_hi = (uint32_t)(Rn >> 32);
+    o.flags = flags;
+    return o;
 }
 
-__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
-    return v;
+// The rare follow-ups of coder_slow that touch the (local-memory) decoder state.
+__device__ __noinline__ uint32_t coder_bookkeeping(const SLoc &S, DecState &c, int lane, uint32_t flags) {
+    if (flags & 1u) dec_advance_word(S, c, lane);
+    if (flags & 2u) c.slow++;
+    if (flags & 4u) c.err = CCD_ERR_DESYNC;
+    return c.wnext;
 }
+
+// One symbol of the recursion, executed IDENTICALLY by every lane of the coder warp: no vote, no
+// shuffle, no shared-memory round trip on the serial chain -- two 64-bit products, one subtraction and
+// one unsigned compare.  h = (left(M), left(M+1) - left(M), ..) of the most probable symbol M:
+// D - scale*left(M) < scale*p(M) (wrapping) <=> the symbol is M;  new R = scale*p(M).
+// Nothing is written for a mode symbol: the helper learns it from `done` and the absence of a result word.
+#ifdef CCD_PROFILE
+#define CODER_COUNT_FAR(F) c.n_far += ((F) >> 3) & 1u
+#define CODER_SLOW_T0 const long long ts_ = clock64()
+#define CODER_SLOW_T1 pc.seg[2] += clock64() - ts_; pc.seg[0]++
+#else
+#define CODER_COUNT_FAR(F)
+#define CODER_SLOW_T0
+#define CODER_SLOW_T1
+#endif
+#define CODER_STEP(JJ, H)                                                                                   \
+    do {                                                                                                    \
+        const uint64_t scale_ = R >> 24;                                                                    \
+        const uint64_t lo_ = scale_ * (H).x;                                                                \
+        const uint64_t rn_ = scale_ * (H).y;                                                                \
+        const uint64_t dn_ = D - lo_;                                                                       \
+        if (dn_ < rn_ && (uint32_t)(rn_ >> 32) != 0u) {                                                     \
+            D = dn_;                                                                                        \
+            R = rn_;                                                                                        \
+        } else {                                                                                            \
+            CODER_SLOW_T0;                                                                                  \
+            const SlowOut r_ = coder_slow(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, (JJ), (H), D, R, wnext); \
+            D = ((uint64_t)r_.d_hi << 32) | r_.d_lo;                                                        \
+            R = ((uint64_t)r_.r_hi << 32) | r_.r_lo;                                                        \
+            CODER_COUNT_FAR(r_.flags);                                                                      \
+            if (r_.flags & 7u) wnext = coder_bookkeeping(S, c, lane, r_.flags);                             \
+            CODER_SLOW_T1;                                                                                  \
+        }                                                                                                   \
+    } while (0)
 
 __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
                                            int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
                                            ProfCounters &pc) {
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
-    const uint32_t ready_a = sm.ctrl + 4u;
+    const uint32_t ready_a = sm.ctrl + 4u, done_a = sm.ctrl + 8u;
     uint64_t D = c.D, R = c.R;
     uint32_t wnext = c.wnext;
     uint32_t j = ord_begin;
@@ -794,8 +860,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
         const uint32_t r = lds_u32(ready_a);
         limit = ((int32_t)(r - ord_end) > 0) ? ord_end : r;
     };
-    // (left(mode), left(mode+1)) = window entries 15, 16 of symbol jj: one 8-byte aligned LDS.64
-    auto mode_of = [&](uint32_t jj) { return lds_v2(sm.win + (jj & ring_mask) * (CCD_WIN * 4) + 4u * CCD_WIN_HALF); };
+    auto hot_of = [&](uint32_t jj) { return lds_v4(sm.hot + (jj & ring_mask) * 16u); };
     while (j != ord_end) {
         if ((int32_t)(limit - j) <= 0) {
             PROF_T(t0);
@@ -805,32 +870,35 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             PROF_ADD(pc.wait, t0);
         }
         if ((int32_t)(limit - j) >= 6) {
-            // steady state, three symbols per round trip through the loop: the cumulatives of
-            // symbols j+3..j+5 are requested while j..j+2 are decoded (no register rotation)
-            uint2 a0 = mode_of(j), a1 = mode_of(j + 1u), a2 = mode_of(j + 2u);
+            // steady state, three symbols per round trip through the loop: the hot entries of symbols
+            // j+3..j+5 are requested while j..j+2 are decoded
+            uint4 a0 = hot_of(j), a1 = hot_of(j + 1u), a2 = hot_of(j + 2u);
             while (true) {
                 if ((int32_t)(limit - j) < 6) {
                     refresh();
                     if ((int32_t)(limit - j) < 6) break;
                 }
-                const uint2 b0 = mode_of(j + 3u), b1 = mode_of(j + 4u), b2 = mode_of(j + 5u);
-                coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c, pc);
-                coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c, pc);
-                coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c, pc);
+                const uint4 b0 = hot_of(j + 3u), b1 = hot_of(j + 4u), b2 = hot_of(j + 5u);
+                CODER_STEP(j, a0);
+                CODER_STEP(j + 1u, a1);
+                CODER_STEP(j + 2u, a2);
                 j += 3u;
+                sts_u32(done_a, j);  // every lane stores the same word: no predicate on the hot path
                 a0 = b0;
                 a1 = b1;
                 a2 = b2;
             }
             // a0..a2 are valid (limit - j >= 3 here)
-            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c, pc);
-            coder_step(S, sm, scale_tab, ring_mask, lane, j + 1u, a1, D, R, wnext, c, pc);
-            coder_step(S, sm, scale_tab, ring_mask, lane, j + 2u, a2, D, R, wnext, c, pc);
+            CODER_STEP(j, a0);
+            CODER_STEP(j + 1u, a1);
+            CODER_STEP(j + 2u, a2);
             j += 3u;
+            sts_u32(done_a, j);
         } else {
-            const uint2 a0 = mode_of(j);
-            coder_step(S, sm, scale_tab, ring_mask, lane, j, a0, D, R, wnext, c, pc);
+            const uint4 a0 = hot_of(j);
+            CODER_STEP(j, a0);
             j++;
+            sts_u32(done_a, j);
         }
     }
     c.D = D;
@@ -864,19 +932,23 @@ __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm,
 #endif
         }
         {
-            const uint32_t jj = p + (uint32_t)lane;
-            bool ok = false;
-            uint32_t w = 0;
-            if ((int32_t)(r - jj) > 0) {
-                w = lds_u32(sm.res + (jj & ring_mask) * 4u);
-                ok = ((w >> 8) & 0x7fffffu) == ((jj + 1u) & 0x7fffffu);
-            }
-            const uint32_t b = __ballot_sync(0xffffffffu, ok);
-            const uint32_t cnt = (b == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~b) - 1);
+            // symbols [p, done) are decoded: mode symbols left no trace, the others a tagged result word
+            const uint32_t d = lds_u32(sm.ctrl + 8u);
+            const int32_t avail = (int32_t)(d - p);
+            const uint32_t cnt = avail <= 0 ? 0u : (avail > 32 ? 32u : (uint32_t)avail);
             if ((uint32_t)lane < cnt) {
-                const uint4 m = lds_v4(sm.meta + (jj & ring_mask) * 16u);
-                const int v = (int)(w & 0xffu);
-                const int sym = (w >> 31) ? (int)(int8_t)v : ((int)(m.y >> 16) - 128 + v);
+                const uint32_t jj = p + (uint32_t)lane;
+                const uint32_t slot = jj & ring_mask;
+                const uint32_t w = lds_u32(sm.res + slot * 4u);
+                const uint4 m = lds_v4(sm.meta + slot * 16u);
+                const bool other = (w & 0x7fffff00u) == res_tag(jj);
+                const int base = (int)(m.y >> 16) - 128;  // s_lo
+                int sym = base + CCD_WIN_HALF;
+                if (other) {
+                    const int v = (int)(w & 0xffu);
+                    sym = (w >> 31) ? (int)(int8_t)v : base + v;
+                    sts_u32(sm.res + slot * 4u, 0u);  // no stale word survives a trip around the ring
+                }
                 sts_u8(sm.rows + (m.y & 0xffffu), sym);
                 S.latents[m.x] = (int8_t)sym;
             }
@@ -1006,6 +1078,7 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     DecState ds;
     ds.err = 0;
     ds.slow = 0;
+    ds.n_far = 0;
     ds.wpos = 2;
     ds.wcur = ds.wnxt = ds.wnext = 0;
     ds.D = 0;
@@ -1061,7 +1134,7 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
             atomicAdd(&G.status[4], (int)(pc.wait >> 10));
             atomicAdd(&G.status[5], (int)(pc.total >> 10));
             G.status[10] = (int)pc.seg[0];
-            G.status[11] = (int)pc.seg[1];
+            G.status[11] = (int)ds.n_far;
             G.status[12] = (int)(pc.seg[2] >> 10);
         }
     }
@@ -1112,7 +1185,8 @@ unsigned long long g_ccd_launches = 0;
 
 size_t ccd_entropy_smem_bytes(int ring, int rows, int arm_blob_bytes, int ifce_blob_max) {
     size_t p = 64 + align16(sizeof(EntGrid)) + align16((size_t)arm_blob_bytes) + align16((size_t)ifce_blob_max);
-    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)ring * 4 + (size_t)rows * CCD_ROW_COLS;
+    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)ring * 16 + (size_t)ring * 4 +
+         (size_t)rows * CCD_ROW_COLS;
     return p;
 }
 

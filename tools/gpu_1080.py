@@ -9,7 +9,12 @@ from coolchic_b200._desc import desc_from_header
 ctx = _native.get_context(0)
 ss = synth.SeedStream(ctx)
 hyp = (4, 6) if len(sys.argv) > 1 and sys.argv[1] == "hyper" else None
-cc, h, lat = synth.make_coolchic(ctx, ss, (1080, 1920), (0, 6), hyp, seed=0)
+zeros = "zeros" in sys.argv
+lat_in = None
+if zeros:  # all-zero latents: (almost) every symbol is the mode -> time per symbol = the coder's hot path
+    tmp_h = synth.make_coolchic_header(ss.header, (1080, 1920), (0, 6), hyp)
+    lat_in = torch.zeros(desc_from_header(tmp_h).n_symbols(), dtype=torch.int8, device="cuda")
+cc, h, lat = synth.make_coolchic(ctx, ss, (1080, 1920), (0, 6), hyp, seed=0, latents=lat_in)
 h2 = type(h)(); rest = h2.read_header(cc); d = desc_from_header(h2)
 nnb = rest[:h2.get_value("nn_n_bytes")]; lb = rest[h2.get_value("nn_n_bytes"):][:h2.get_value("n_bytes_latent")]
 nn = _native.decode_nn(d, nnb)

@@ -18,4 +18,4 @@ for it in range(3):
     lat = ctx.decode_latents(d, nn, lb); torch.cuda.synchronize()
     st = ctx.last_status()
     print(ctx.last_timing(), "ok" if np.array_equal(lat.cpu().numpy(), g) else "MISMATCH")
-    print(" status", st[:4], "| coder wait %d total %d kcyc | producers(sum of 15 warps) wait %d arm %d win %d total %d kcyc" % tuple(st[4:10]))
+    print(" status", st[:4], "| coder wait %d total %d kcyc | producers(sum of 15 warps) wait %d arm %d win %d total %d kcyc" % tuple(st[4:10]), "ext", st[10:16])
