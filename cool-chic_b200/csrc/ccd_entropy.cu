@@ -200,7 +200,7 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int r
     L.win = base_a + (uint32_t)p;
     p += (size_t)ring * CCD_WIN * 4;
     L.hot = base_a + (uint32_t)p;
-    p += (size_t)ring * 16;
+    p += (size_t)(ring + CCD_HOT_MIRROR) * 16;  // entries 0..7 are mirrored after the end: +32 B never wraps
     L.res = base_a + (uint32_t)p;
     p += (size_t)ring * 4;
     L.rows = base_a + (uint32_t)p;
@@ -520,11 +520,19 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
             // hot entry (the coder's steady state reads nothing else): window entries 13 .. 16
             static_assert(CCD_WIN_HALF == 14, "hot entry layout");
             const uint32_t hdst = sm.hot + slot * 16u;
+            const bool mirror = slot < CCD_HOT_MIRROR;
+            const uint32_t hmir = hdst + (uint32_t)S.ring * 16u;
             if (member == 1) {
                 sts_v2(hdst, make_uint2(fb.z, fb.w - fb.z));
                 sts_u32(hdst + 8u, fb.y);
+                if (mirror) {
+                    sts_v2(hmir, make_uint2(fb.z, fb.w - fb.z));
+                    sts_u32(hmir + 8u, fb.y);
+                }
             } else if (member == 2) {
-                sts_u32(hdst + 12u, fix_left(va.x, s0));
+                const uint32_t l16 = fix_left(va.x, s0);
+                sts_u32(hdst + 12u, l16);
+                if (mirror) sts_u32(hmir + 12u, l16);
             }
         }
         __threadfence_block();
@@ -542,6 +550,7 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
                 const uint32_t l13 = fix_left(v[3].y, s_lo + 13), l14 = fix_left(v[3].z, s_lo + 14);
                 const uint32_t l15 = fix_left(v[3].w, s_lo + 15), l16 = fix_left(v[4].x, s_lo + 16);
                 sts_v4(sm.hot + slot * 16u, make_uint4(l14, l15 - l14, l13, l16));
+                if (slot < CCD_HOT_MIRROR) sts_v4(sm.hot + (slot + (uint32_t)S.ring) * 16u, make_uint4(l14, l15 - l14, l13, l16));
             }
             __threadfence_block();
         }
@@ -827,23 +836,112 @@ __device__ __noinline__ uint32_t coder_bookkeeping(const SLoc &S, DecState &c, i
 #define CODER_SLOW_T0
 #define CODER_SLOW_T1
 #endif
-#define CODER_STEP(JJ, H)                                                                                   \
+// The test: with Dn = D - scale*left(M) (wrapping) and Rn = scale*p(M), "symbol is M and no
+// renormalisation" <=> Dn < Rn and Rn >= 2^32.  hi32(Dn) < hi32(Rn) implies both; the converse fails only
+// when the two high words are equal (probability ~ 1 / hi32(Rn)): those go to coder_slow too, which decides
+// exactly.  One 32-bit compare per symbol instead of a 64-bit compare chain plus a range test.
+//
+// Software pipelining: the branch of symbol j has to wait for that compare, so the products of symbol
+// j+1 are issued BEFORE it, from Rn (the state if j is the mode, the common case), and redone after
+// coder_slow otherwise.  The loop-carried chain is R -> shift -> multiply -> R.
+#define CODER_SLOW(JJ, H)                                                                                   \
+    do {                                                                                                    \
+        CODER_SLOW_T0;                                                                                      \
+        const SlowOut r_ = coder_slow(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, (JJ), (H), D, R, wnext); \
+        D = ((uint64_t)r_.d_hi << 32) | r_.d_lo;                                                            \
+        R = ((uint64_t)r_.r_hi << 32) | r_.r_lo;                                                            \
+        CODER_COUNT_FAR(r_.flags);                                                                          \
+        if (r_.flags & 7u) wnext = coder_bookkeeping(S, c, lane, r_.flags);                                 \
+        CODER_SLOW_T1;                                                                                      \
+    } while (0)
+// products of a symbol from the current R
+#define CODER_PRE(H)                                                                                        \
     do {                                                                                                    \
         const uint64_t scale_ = R >> 24;                                                                    \
-        const uint64_t lo_ = scale_ * (H).x;                                                                \
-        const uint64_t rn_ = scale_ * (H).y;                                                                \
-        const uint64_t dn_ = D - lo_;                                                                       \
-        if (dn_ < rn_ && (uint32_t)(rn_ >> 32) != 0u) {                                                     \
+        lo = scale_ * (H).x;                                                                                \
+        rn = scale_ * (H).y;                                                                                \
+    } while (0)
+// symbol JJ (products in lo, rn), then the products of the next symbol (hot entry HN).  Written in PTX
+// and volatile so that the look-ahead products stay ABOVE the branch (the compiler otherwise proves
+// them equal to CODER_PRE after the join and sinks them below it, back onto the serial chain).
+__device__ __forceinline__ uint32_t coder_spec(uint64_t D, uint64_t lo, uint64_t rn, uint32_t nL, uint32_t nP, uint64_t &dn,
+                                           uint64_t &lo2, uint64_t &rn2) {
+    uint32_t dn_lo, dn_hi, l2_lo, l2_hi, r2_lo, r2_hi, ok;
+    asm volatile(
+        "{\n"
+        " .reg .u32 s_lo, s_hi, t;\n"
+        " .reg .pred p;\n"
+        " sub.cc.u32 %0, %7, %9;\n"
+        " subc.u32 %1, %8, %10;\n"
+        " shf.r.clamp.b32 s_lo, %11, %12, 24;\n"
+        " shr.u32 s_hi, %12, 24;\n"
+        " mul.lo.u32 %2, s_lo, %13;\n"
+        " mul.hi.u32 t, s_lo, %13;\n"
+        " mad.lo.u32 %3, s_hi, %13, t;\n"
+        " mul.lo.u32 %4, s_lo, %14;\n"
+        " mul.hi.u32 t, s_lo, %14;\n"
+        " mad.lo.u32 %5, s_hi, %14, t;\n"
+        " setp.lt.u32 p, %1, %12;\n"
+        " selp.u32 %6, 1, 0, p;\n"
+        "}\n"
+        : "=r"(dn_lo), "=r"(dn_hi), "=r"(l2_lo), "=r"(l2_hi), "=r"(r2_lo), "=r"(r2_hi), "=r"(ok)
+        : "r"((uint32_t)D), "r"((uint32_t)(D >> 32)), "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"((uint32_t)rn),
+          "r"((uint32_t)(rn >> 32)), "r"(nL), "r"(nP));
+    dn = ((uint64_t)dn_hi << 32) | dn_lo;
+    lo2 = ((uint64_t)l2_hi << 32) | l2_lo;
+    rn2 = ((uint64_t)r2_hi << 32) | r2_lo;
+    return ok;
+}
+#define CODER_STEP_SPEC(JJ, H, HN)                                                                          \
+    do {                                                                                                    \
+        uint64_t dn_, lo2_, rn2_;                                                                           \
+        if (coder_spec(D, lo, rn, (HN).x, (HN).y, dn_, lo2_, rn2_)) {                                       \
             D = dn_;                                                                                        \
-            R = rn_;                                                                                        \
+            R = rn;                                                                                         \
+            lo = lo2_;                                                                                      \
+            rn = rn2_;                                                                                      \
         } else {                                                                                            \
-            CODER_SLOW_T0;                                                                                  \
-            const SlowOut r_ = coder_slow(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, (JJ), (H), D, R, wnext); \
-            D = ((uint64_t)r_.d_hi << 32) | r_.d_lo;                                                        \
-            R = ((uint64_t)r_.r_hi << 32) | r_.r_lo;                                                        \
-            CODER_COUNT_FAR(r_.flags);                                                                      \
-            if (r_.flags & 7u) wnext = coder_bookkeeping(S, c, lane, r_.flags);                             \
-            CODER_SLOW_T1;                                                                                  \
+            CODER_SLOW(JJ, H);                                                                              \
+            CODER_PRE(HN);                                                                                  \
+        }                                                                                                   \
+    } while (0)
+// Three symbols (hot entries H0..H2, products of H0 in lo / rn), each assuming its predecessors were the
+// mode, plus the products of the symbol after them (HN); one branch.  On a miss: commit the symbols before
+// the first miss (selects) and hand it to coder_exact.
+#define CODER_TRIPLE(JB, H0, H1, H2, HN)                                                                    \
+    do {                                                                                                    \
+        uint64_t dn0_, lo1_, rn1_, dn1_, lo2_, rn2_, dn2_, lo3_, rn3_;                                      \
+        const uint32_t k0_ = coder_spec(D, lo, rn, (H1).x, (H1).y, dn0_, lo1_, rn1_);                       \
+        const uint32_t k1_ = coder_spec(dn0_, lo1_, rn1_, (H2).x, (H2).y, dn1_, lo2_, rn2_);                \
+        const uint32_t k2_ = coder_spec(dn1_, lo2_, rn2_, (HN).x, (HN).y, dn2_, lo3_, rn3_);                \
+        if (__builtin_expect((k0_ & k1_ & k2_) != 0u, 1)) {                                                 \
+            D = dn2_;                                                                                       \
+            R = rn2_;                                                                                       \
+            lo = lo3_;                                                                                      \
+            rn = rn3_;                                                                                      \
+        } else {                                                                                            \
+            const bool c0_ = k0_ != 0u, c1_ = (k0_ & k1_) != 0u;                                            \
+            if (c0_) {                                                                                      \
+                D = c1_ ? dn1_ : dn0_;                                                                      \
+                R = c1_ ? rn1_ : rn;                                                                        \
+            }                                                                                               \
+            hf.x = c0_ ? (c1_ ? (H2).x : (H1).x) : (H0).x;                                                  \
+            hf.y = c0_ ? (c1_ ? (H2).y : (H1).y) : (H0).y;                                                  \
+            hf.z = c0_ ? (c1_ ? (H2).z : (H1).z) : (H0).z;                                                  \
+            hf.w = c0_ ? (c1_ ? (H2).w : (H1).w) : (H0).w;                                                  \
+            jf = (JB) + (c0_ ? (c1_ ? 2u : 1u) : 0u);                                                       \
+            goto coder_exact;                                                                               \
+        }                                                                                                   \
+    } while (0)
+// symbol JJ (products in lo, rn) without look-ahead
+#define CODER_STEP_LAST(JJ, H)                                                                              \
+    do {                                                                                                    \
+        const uint64_t dn_ = D - lo;                                                                        \
+        if ((uint32_t)(dn_ >> 32) < (uint32_t)(rn >> 32)) {                                                 \
+            D = dn_;                                                                                        \
+            R = rn;                                                                                         \
+        } else {                                                                                            \
+            CODER_SLOW(JJ, H);                                                                              \
         }                                                                                                   \
     } while (0)
 
@@ -853,6 +951,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
     const uint32_t ready_a = sm.ctrl + 4u, done_a = sm.ctrl + 8u;
     uint64_t D = c.D, R = c.R;
+    uint64_t lo = 0, rn = 0;
     uint32_t wnext = c.wnext;
     uint32_t j = ord_begin;
     uint32_t limit = ord_begin;  // symbols < limit have their window in the ring
@@ -862,6 +961,8 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     };
     auto hot_of = [&](uint32_t jj) { return lds_v4(sm.hot + (jj & ring_mask) * 16u); };
     while (j != ord_end) {
+        uint4 hf;     // inputs of coder_exact
+        uint32_t jf;
         if ((int32_t)(limit - j) <= 0) {
             PROF_T(t0);
             do {
@@ -869,37 +970,93 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             } while ((int32_t)(limit - j) <= 0);
             PROF_ADD(pc.wait, t0);
         }
-        if ((int32_t)(limit - j) >= 6) {
-            // steady state, three symbols per round trip through the loop: the hot entries of symbols
-            // j+3..j+5 are requested while j..j+2 are decoded
-            uint4 a0 = hot_of(j), a1 = hot_of(j + 1u), a2 = hot_of(j + 2u);
+        if ((int32_t)(limit - j) >= 9) {
+            // Steady state.  Branches are what costs on this warp (~30 cycles each: predicate wait + fetch
+            // redirect, measured), so a TRIPLE of symbols is decoded speculatively -- each one assuming
+            // its predecessors were the mode -- and checked with ONE branch.  Six symbols per round trip:
+            // the hot entries of the next triple are requested while a triple is decoded and the two
+            // register sets swap roles (no copies); the ring's first entries are mirrored behind its
+            // end, so one address serves a triple.  When a triple fails, the symbols before the first
+            // miss are committed, the miss is decoded exactly (coder_exact below) and the loop
+            // re-aligns on the symbol after it.
+            uint32_t o = sm.hot + (j & ring_mask) * 16u;
+            uint4 a0 = lds_v4(o), a1 = lds_v4(o + 16u), a2 = lds_v4(o + 32u);
+            CODER_PRE(a0);
             while (true) {
-                if ((int32_t)(limit - j) < 6) {
+                if ((int32_t)(limit - j) < 9) {
                     refresh();
-                    if ((int32_t)(limit - j) < 6) break;
+                    if ((int32_t)(limit - j) < 9) break;
                 }
-                const uint4 b0 = hot_of(j + 3u), b1 = hot_of(j + 4u), b2 = hot_of(j + 5u);
-                CODER_STEP(j, a0);
-                CODER_STEP(j + 1u, a1);
-                CODER_STEP(j + 2u, a2);
-                j += 3u;
-                sts_u32(done_a, j);  // every lane stores the same word: no predicate on the hot path
-                a0 = b0;
-                a1 = b1;
-                a2 = b2;
+                o = sm.hot + ((j + 3u) & ring_mask) * 16u;
+                const uint4 b0 = lds_v4(o), b1 = lds_v4(o + 16u), b2 = lds_v4(o + 32u);
+                CODER_TRIPLE(j, a0, a1, a2, b0);
+                sts_u32(done_a, j + 3u);  // every lane stores the same word: no predicate on the hot path
+                o = sm.hot + ((j + 6u) & ring_mask) * 16u;
+                a0 = lds_v4(o);
+                a1 = lds_v4(o + 16u);
+                a2 = lds_v4(o + 32u);
+                CODER_TRIPLE(j + 3u, b0, b1, b2, a0);
+                j += 6u;
+                sts_u32(done_a, j);
+#ifdef CCD_PROFILE
+                pc.seg[3] += 6;
+#endif
             }
-            // a0..a2 are valid (limit - j >= 3 here)
-            CODER_STEP(j, a0);
-            CODER_STEP(j + 1u, a1);
-            CODER_STEP(j + 2u, a2);
-            j += 3u;
-            sts_u32(done_a, j);
+            continue;  // fewer than 9 symbols ready: one at a time (below) until the producers are ahead again
         } else {
             const uint4 a0 = hot_of(j);
-            CODER_STEP(j, a0);
+            CODER_PRE(a0);
+            CODER_STEP_LAST(j, a0);
             j++;
             sts_u32(done_a, j);
+#ifdef CCD_PROFILE
+            pc.seg[4]++;
+#endif
         }
+        continue;
+    coder_exact : {
+        // Symbol jf (hot entry hf) from the exact state (D, R): the mode after all (equal high words), one of
+        // its two neighbours (selects, no branch), or anything else (coder_far, rare); result word for the
+        // helper; renormalisation.
+        constexpr uint32_t M = CCD_WIN_HALF;
+        CODER_SLOW_T0;
+        const uint64_t scale_ = R >> 24;
+        const uint64_t lo_ = scale_ * hf.x, rn_ = scale_ * hf.y;
+        const uint64_t hi_ = lo_ + rn_;  // = scale * left(M + 1)
+        const uint64_t p1_ = scale_ * hf.z, q2_ = scale_ * hf.w;
+        const bool is_m = (D - lo_) < rn_;
+        const bool is_l = (p1_ <= D) & (D < lo_);
+        const bool is_r = (hi_ <= D) & (D < q2_);
+        uint64_t nlo = is_m ? lo_ : (is_l ? p1_ : hi_);
+        uint64_t nhi = is_m ? hi_ : (is_l ? lo_ : q2_);
+        uint32_t rw = res_tag(jf) | (is_l ? (M - 1u) : (M + 1u));
+        const uint32_t slot = jf & ring_mask;
+        uint32_t flags = 0;
+        if (!(is_m | is_l | is_r)) {
+            const FarOut f = coder_far(sm.win + slot * (CCD_WIN * 4), sm.meta + slot * 16u, scale_tab, lane, jf, scale_, D);
+            nlo = f.lo;
+            nhi = f.hi;
+            rw = f.rw;
+            flags = f.flags;
+        }
+        D -= nlo;
+        R = nhi - nlo;
+        // shared-memory stores of one warp are performed in program order: this word is visible before the
+        // `done` store that follows it
+        if (!is_m && lane == 0) sts_u32(sm.res + slot * 4u, rw);
+#ifdef CCD_PROFILE
+        c.n_far += is_m ? 0u : 1u;
+#endif
+        if ((R >> 32) == 0) {  // at most one renormalisation per symbol
+            R <<= 32;
+            D = (D << 32) | wnext;
+            flags |= 1u;
+        }
+        if (flags) wnext = coder_bookkeeping(S, c, lane, flags);
+        j = jf + 1u;
+        sts_u32(done_a, j);
+        CODER_SLOW_T1;
+    }
     }
     c.D = D;
     c.R = R;
@@ -1136,6 +1293,8 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
             G.status[10] = (int)pc.seg[0];
             G.status[11] = (int)ds.n_far;
             G.status[12] = (int)(pc.seg[2] >> 10);
+            G.status[13] = (int)pc.seg[3];  // symbols decoded in the steady loop
+            G.status[14] = (int)pc.seg[4];  // symbols decoded one at a time (coder close behind the producers)
         }
     }
 #endif
@@ -1185,7 +1344,7 @@ unsigned long long g_ccd_launches = 0;
 
 size_t ccd_entropy_smem_bytes(int ring, int rows, int arm_blob_bytes, int ifce_blob_max) {
     size_t p = 64 + align16(sizeof(EntGrid)) + align16((size_t)arm_blob_bytes) + align16((size_t)ifce_blob_max);
-    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)ring * 16 + (size_t)ring * 4 +
+    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)(ring + CCD_HOT_MIRROR) * 16 + (size_t)ring * 4 +
          (size_t)rows * CCD_ROW_COLS;
     return p;
 }

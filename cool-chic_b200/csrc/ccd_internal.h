@@ -15,6 +15,7 @@
 #define CCD_WIN 32                   // cumulative-window entries per symbol (31 decodable symbols)
 #define CCD_WIN_HALF 14              // window = symbols mu_int-14 .. mu_int+16; the mode sits at the EVEN index 14
                                      // so that (left(mode), left(mode+1)) is one aligned LDS.64
+#define CCD_HOT_MIRROR 8            // hot-ring entries duplicated behind the end of the ring
 #define CCD_ROW_COLS 64              // row ring: columns kept per row (power of 2)
 #define CCD_IFCE_FAST_MAX 12         // IFCE inputs handled by the fast (quad) kernel; more -> generic kernel
 #define CCD_MAX_DIM 72               // n_ctx (<=40) + n_ifce_out (<=31)
