@@ -757,54 +757,37 @@ struct SlowOut {
 __device__ __noinline__ SlowOut coder_slow(uint32_t res_a, uint32_t win_a, uint32_t meta_a,
                                            const float *__restrict__ scale_tab, uint32_t ring_mask, int lane, uint32_t j,
                                            uint4 h, uint64_t D, uint64_t R, uint32_t wnext) {
+    // Branches are what costs on this warp (~30 cycles each: predicate wait + fetch redirect, measured), so
+    // the mode and its two neighbours are decided with selects; only "none of the three" and the
+    // renormalisation bookkeeping branch (both rare).
     constexpr uint32_t M = CCD_WIN_HALF;
     const uint64_t scale = R >> 24;
-    uint64_t lo = scale * h.x;
-    uint64_t Rn = scale * h.y;
-    uint64_t Dn = D - lo;
-    uint32_t flags = 0;
-    if (!(Dn < Rn)) {
-        flags = 8;
-        const uint64_t hiM = lo + Rn;  // = scale * left(M + 1)
-        const uint32_t slot = j & ring_mask;
-        uint64_t hi = 0;
-        uint32_t rw = 0;
-        bool found = false;
-        if (D < lo) {
-            const uint64_t p1 = scale * h.z;
-            if (p1 <= D) {
-                hi = lo;
-                lo = p1;
-                rw = res_word(j, M - 1u, false);
-                found = true;
-            }
-        } else {
-            const uint64_t q2 = scale * h.w;
-            if (D < q2) {
-                lo = hiM;
-                hi = q2;
-                rw = res_word(j, M + 1u, false);
-                found = true;
-            }
-        }
-        if (!found) {
-            const FarOut f = coder_far(win_a + slot * (CCD_WIN * 4), meta_a + slot * 16u, scale_tab, lane, j, scale, D);
-            lo = f.lo;
-            hi = f.hi;
-            rw = f.rw;
-            flags |= f.flags;
-        }
-        Dn = D - lo;
-        Rn = hi - lo;
-        // shared-memory stores of one warp are performed in program order: this word is visible before the
-        // `done` store that follows it
-        if (lane == 0) sts_u32(res_a + slot * 4u, rw);
+    const uint64_t lo = scale * h.x, rn = scale * h.y;
+    const uint64_t hiM = lo + rn;  // = scale * left(M + 1)
+    const uint64_t p1 = scale * h.z, q2 = scale * h.w;
+    const bool is_m = (D - lo) < rn;
+    const bool is_l = (p1 <= D) & (D < lo);
+    const bool is_r = (hiM <= D) & (D < q2);
+    uint64_t nlo = is_m ? lo : (is_l ? p1 : hiM);
+    uint64_t nhi = is_m ? hiM : (is_l ? lo : q2);
+    uint32_t rw = res_tag(j) | (is_l ? (M - 1u) : (M + 1u));
+    const uint32_t slot = j & ring_mask;
+    uint32_t flags = is_m ? 0u : 8u;
+    if (!(is_m | is_l | is_r)) {
+        const FarOut f = coder_far(win_a + slot * (CCD_WIN * 4), meta_a + slot * 16u, scale_tab, lane, j, scale, D);
+        nlo = f.lo;
+        nhi = f.hi;
+        rw = f.rw;
+        flags |= f.flags;
     }
-    if ((Rn >> 32) == 0) {  // at most one renormalisation per symbol
-        Rn <<= 32;
-        Dn = (Dn << 32) | wnext;
-        flags |= 1;
-    }
+    uint64_t Dn = D - nlo, Rn = nhi - nlo;
+    // shared-memory stores of one warp are performed in program order: this word is visible before the
+    // `done` store that follows it
+    if (!is_m && lane == 0) sts_u32(res_a + slot * 4u, rw);
+    const bool renorm = (Rn >> 32) == 0;  // at most one renormalisation per symbol
+    Dn = renorm ? ((Dn << 32) | wnext) : Dn;
+    Rn = renorm ? (Rn << 32) : Rn;
+    flags |= renorm ? 1u : 0u;
     SlowOut o;
     o.d_lo = (uint32_t)Dn;
     o.d_hi = (uint32_t)(Dn >> 32);
@@ -895,7 +878,7 @@ __device__ __forceinline__ uint32_t coder_spec(uint64_t D, uint64_t lo, uint64_t
 #define CODER_STEP_SPEC(JJ, H, HN)                                                                          \
     do {                                                                                                    \
         uint64_t dn_, lo2_, rn2_;                                                                           \
-        if (coder_spec(D, lo, rn, (HN).x, (HN).y, dn_, lo2_, rn2_)) {                                       \
+        if (__builtin_expect(coder_spec(D, lo, rn, (HN).x, (HN).y, dn_, lo2_, rn2_) != 0u, 1)) {                                       \
             D = dn_;                                                                                        \
             R = rn;                                                                                         \
             lo = lo2_;                                                                                      \
@@ -903,34 +886,6 @@ __device__ __forceinline__ uint32_t coder_spec(uint64_t D, uint64_t lo, uint64_t
         } else {                                                                                            \
             CODER_SLOW(JJ, H);                                                                              \
             CODER_PRE(HN);                                                                                  \
-        }                                                                                                   \
-    } while (0)
-// Three symbols (hot entries H0..H2, products of H0 in lo / rn), each assuming its predecessors were the
-// mode, plus the products of the symbol after them (HN); one branch.  On a miss: commit the symbols before
-// the first miss (selects) and hand it to coder_exact.
-#define CODER_TRIPLE(JB, H0, H1, H2, HN)                                                                    \
-    do {                                                                                                    \
-        uint64_t dn0_, lo1_, rn1_, dn1_, lo2_, rn2_, dn2_, lo3_, rn3_;                                      \
-        const uint32_t k0_ = coder_spec(D, lo, rn, (H1).x, (H1).y, dn0_, lo1_, rn1_);                       \
-        const uint32_t k1_ = coder_spec(dn0_, lo1_, rn1_, (H2).x, (H2).y, dn1_, lo2_, rn2_);                \
-        const uint32_t k2_ = coder_spec(dn1_, lo2_, rn2_, (HN).x, (HN).y, dn2_, lo3_, rn3_);                \
-        if (__builtin_expect((k0_ & k1_ & k2_) != 0u, 1)) {                                                 \
-            D = dn2_;                                                                                       \
-            R = rn2_;                                                                                       \
-            lo = lo3_;                                                                                      \
-            rn = rn3_;                                                                                      \
-        } else {                                                                                            \
-            const bool c0_ = k0_ != 0u, c1_ = (k0_ & k1_) != 0u;                                            \
-            if (c0_) {                                                                                      \
-                D = c1_ ? dn1_ : dn0_;                                                                      \
-                R = c1_ ? rn1_ : rn;                                                                        \
-            }                                                                                               \
-            hf.x = c0_ ? (c1_ ? (H2).x : (H1).x) : (H0).x;                                                  \
-            hf.y = c0_ ? (c1_ ? (H2).y : (H1).y) : (H0).y;                                                  \
-            hf.z = c0_ ? (c1_ ? (H2).z : (H1).z) : (H0).z;                                                  \
-            hf.w = c0_ ? (c1_ ? (H2).w : (H1).w) : (H0).w;                                                  \
-            jf = (JB) + (c0_ ? (c1_ ? 2u : 1u) : 0u);                                                       \
-            goto coder_exact;                                                                               \
         }                                                                                                   \
     } while (0)
 // symbol JJ (products in lo, rn) without look-ahead
@@ -961,8 +916,6 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     };
     auto hot_of = [&](uint32_t jj) { return lds_v4(sm.hot + (jj & ring_mask) * 16u); };
     while (j != ord_end) {
-        uint4 hf;     // inputs of coder_exact
-        uint32_t jf;
         if ((int32_t)(limit - j) <= 0) {
             PROF_T(t0);
             do {
@@ -971,14 +924,9 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             PROF_ADD(pc.wait, t0);
         }
         if ((int32_t)(limit - j) >= 9) {
-            // Steady state.  Branches are what costs on this warp (~30 cycles each: predicate wait + fetch
-            // redirect, measured), so a TRIPLE of symbols is decoded speculatively -- each one assuming
-            // its predecessors were the mode -- and checked with ONE branch.  Six symbols per round trip:
-            // the hot entries of the next triple are requested while a triple is decoded and the two
-            // register sets swap roles (no copies); the ring's first entries are mirrored behind its
-            // end, so one address serves a triple.  When a triple fails, the symbols before the first
-            // miss are committed, the miss is decoded exactly (coder_exact below) and the loop
-            // re-aligns on the symbol after it.
+            // steady state, six symbols per round trip through the loop: the hot entries of the next triple
+            // are requested while a triple is decoded, and the two register sets swap roles (no copies);
+            // the ring's first entries are mirrored behind its end, so one address serves a triple
             uint32_t o = sm.hot + (j & ring_mask) * 16u;
             uint4 a0 = lds_v4(o), a1 = lds_v4(o + 16u), a2 = lds_v4(o + 32u);
             CODER_PRE(a0);
@@ -989,20 +937,29 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
                 }
                 o = sm.hot + ((j + 3u) & ring_mask) * 16u;
                 const uint4 b0 = lds_v4(o), b1 = lds_v4(o + 16u), b2 = lds_v4(o + 32u);
-                CODER_TRIPLE(j, a0, a1, a2, b0);
+                CODER_STEP_SPEC(j, a0, a1);
+                CODER_STEP_SPEC(j + 1u, a1, a2);
+                CODER_STEP_SPEC(j + 2u, a2, b0);
                 sts_u32(done_a, j + 3u);  // every lane stores the same word: no predicate on the hot path
                 o = sm.hot + ((j + 6u) & ring_mask) * 16u;
                 a0 = lds_v4(o);
                 a1 = lds_v4(o + 16u);
                 a2 = lds_v4(o + 32u);
-                CODER_TRIPLE(j + 3u, b0, b1, b2, a0);
+                CODER_STEP_SPEC(j + 3u, b0, b1);
+                CODER_STEP_SPEC(j + 4u, b1, b2);
+                CODER_STEP_SPEC(j + 5u, b2, a0);
                 j += 6u;
                 sts_u32(done_a, j);
 #ifdef CCD_PROFILE
                 pc.seg[3] += 6;
 #endif
             }
-            continue;  // fewer than 9 symbols ready: one at a time (below) until the producers are ahead again
+            // a0..a2 are valid (limit - j >= 3 here), lo / rn belong to a0
+            CODER_STEP_SPEC(j, a0, a1);
+            CODER_STEP_SPEC(j + 1u, a1, a2);
+            CODER_STEP_LAST(j + 2u, a2);
+            j += 3u;
+            sts_u32(done_a, j);
         } else {
             const uint4 a0 = hot_of(j);
             CODER_PRE(a0);
@@ -1013,50 +970,6 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             pc.seg[4]++;
 #endif
         }
-        continue;
-    coder_exact : {
-        // Symbol jf (hot entry hf) from the exact state (D, R): the mode after all (equal high words), one of
-        // its two neighbours (selects, no branch), or anything else (coder_far, rare); result word for the
-        // helper; renormalisation.
-        constexpr uint32_t M = CCD_WIN_HALF;
-        CODER_SLOW_T0;
-        const uint64_t scale_ = R >> 24;
-        const uint64_t lo_ = scale_ * hf.x, rn_ = scale_ * hf.y;
-        const uint64_t hi_ = lo_ + rn_;  // = scale * left(M + 1)
-        const uint64_t p1_ = scale_ * hf.z, q2_ = scale_ * hf.w;
-        const bool is_m = (D - lo_) < rn_;
-        const bool is_l = (p1_ <= D) & (D < lo_);
-        const bool is_r = (hi_ <= D) & (D < q2_);
-        uint64_t nlo = is_m ? lo_ : (is_l ? p1_ : hi_);
-        uint64_t nhi = is_m ? hi_ : (is_l ? lo_ : q2_);
-        uint32_t rw = res_tag(jf) | (is_l ? (M - 1u) : (M + 1u));
-        const uint32_t slot = jf & ring_mask;
-        uint32_t flags = 0;
-        if (!(is_m | is_l | is_r)) {
-            const FarOut f = coder_far(sm.win + slot * (CCD_WIN * 4), sm.meta + slot * 16u, scale_tab, lane, jf, scale_, D);
-            nlo = f.lo;
-            nhi = f.hi;
-            rw = f.rw;
-            flags = f.flags;
-        }
-        D -= nlo;
-        R = nhi - nlo;
-        // shared-memory stores of one warp are performed in program order: this word is visible before the
-        // `done` store that follows it
-        if (!is_m && lane == 0) sts_u32(sm.res + slot * 4u, rw);
-#ifdef CCD_PROFILE
-        c.n_far += is_m ? 0u : 1u;
-#endif
-        if ((R >> 32) == 0) {  // at most one renormalisation per symbol
-            R <<= 32;
-            D = (D << 32) | wnext;
-            flags |= 1u;
-        }
-        if (flags) wnext = coder_bookkeeping(S, c, lane, flags);
-        j = jf + 1u;
-        sts_u32(done_a, j);
-        CODER_SLOW_T1;
-    }
     }
     c.D = D;
     c.R = R;
