@@ -28,7 +28,7 @@ EXPORTS = [
     "ccd_version", "ccd_sizeof_desc", "ccd_last_error", "ccd_create", "ccd_destroy", "ccd_nn_count",
     "ccd_latent_count", "ccd_decode_nn", "ccd_decode_many", "ccd_decode_coolchic", "ccd_decode_latents",
     "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict",
-    "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_debug_launch_count", "ccd_debug_set_producer_mask", "ccd_last_timing",
+    "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_debug_launch_count", "ccd_debug_set_producer_mask", "ccd_debug_set_fused_synthesis", "ccd_last_timing",
 ]
 
 
@@ -105,6 +105,8 @@ def load_library():
         L.ccd_debug_launch_count.argtypes = []
         L.ccd_debug_set_producer_mask.restype = ci
         L.ccd_debug_set_producer_mask.argtypes = [vp, ctypes.c_uint32]
+        L.ccd_debug_set_fused_synthesis.restype = ci
+        L.ccd_debug_set_fused_synthesis.argtypes = [vp, ci]
         L.ccd_last_timing.restype = ci
         L.ccd_last_timing.argtypes = [vp, vp]
         if L.ccd_sizeof_desc() != ctypes.sizeof(CcdCoolChicDesc):
@@ -286,6 +288,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.ccd_debug_launch_count())
+
+    def set_fused_synthesis(self, on: bool) -> None:
+        """Debug switch: fused synthesis kernel (default) vs one kernel per layer; results are bit-identical."""
+        _check(self._lib.ccd_debug_set_fused_synthesis(self._h, int(bool(on))))
 
     def last_status(self):
         st = (ctypes.c_int32 * 16)()

@@ -408,6 +408,7 @@ struct CcdContext {
     int32_t last_status[16] = {0};
     uint64_t last_upload_bytes = 0;
     uint32_t prod_mask = 0x3777u;  // warps 3, 7, 11 stay idle: the coder warp (15) owns its scheduler
+    int fused_synthesis = 1;       // 0: layer-by-layer kernels (ccd_debug_set_fused_synthesis, tests compare both)
 };
 
 namespace {
@@ -737,6 +738,25 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
         Ld.b = d_synw + P.syn_off_b[l];
         return Ld;
     };
+    const bool same = (h0 == d->img_h && w0 == d->img_w);
+    SynLayerDev Lo{C, C, 1, 0, 0, d_synw + P.syn_off_ot_w, d_synw + P.syn_off_ot_b};
+    bool fused_done = false;
+    if (ctx->fused_synthesis) {
+        // one kernel for the whole synthesis when the architecture is in the fused family
+        SynLayerDev Ls{L.syn_stab_in, C, 1, 0, 0, d_synw + P.syn_off_st_w, d_synw + P.syn_off_st_b};
+        SynLayerDev all[CCD_MAX_SYN];
+        int in_ft0 = d->syn_in;
+        for (int l = 0; l < d->n_syn_layers; l++) {
+            all[l] = layer(l, in_ft0);
+            in_ft0 = d->syn_out[l];
+        }
+        rc = ccd_syn_fused(cur, h0, w0, d->syn_in, all, d->n_syn_layers, d->syn_stab ? &Ls : nullptr, Lo,
+                           same ? d_out : bufa, st);
+        if (rc > 0) return fail(CCD_ERR_CUDA, "fused synthesis launch");
+        fused_done = (rc == 0);
+    }
+    float *ot_dst = same ? d_out : bufa;
+    if (!fused_done) {
     if (d->syn_stab) {
         SynLayerDev Ls{L.syn_stab_in, C, 1, 0, 0, d_synw + P.syn_off_st_w, d_synw + P.syn_off_st_b};
         if ((rc = ccd_syn_layer(cur, h0, w0, Ls, stab, st))) return fail(CCD_ERR_CUDA, "stabiliser launch");
@@ -762,10 +782,9 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
     if (trunk == cur) return fail(CCD_ERR_ARG, "synthesis without layers");
     if (d->syn_stab)
         if ((rc = ccd_syn_add(trunk, stab, plane * (size_t)C, st))) return fail(CCD_ERR_CUDA, "add launch");
-    SynLayerDev Lo{C, C, 1, 0, 0, d_synw + P.syn_off_ot_w, d_synw + P.syn_off_ot_b};
-    const bool same = (h0 == d->img_h && w0 == d->img_w);
-    float *ot_dst = same ? d_out : dst;
+    ot_dst = same ? d_out : dst;
     if ((rc = ccd_syn_layer(trunk, h0, w0, Lo, ot_dst, st))) return fail(CCD_ERR_CUDA, "output transform launch");
+    }
     if (!same) {
         // final F.interpolate (component/coolchic.py:187-192)
         if (d->final_ups == 0)
@@ -1091,6 +1110,12 @@ int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *ou
 }
 
 uint64_t ccd_debug_launch_count(void) { return g_ccd_launches; }
+
+int ccd_debug_set_fused_synthesis(CcdContext *ctx, int on) {
+    if (!ctx) return fail(CCD_ERR_ARG, "null context");
+    ctx->fused_synthesis = on ? 1 : 0;
+    return CCD_OK;
+}
 
 int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask) {
     if (!ctx || (mask & 0x3fffu) == 0) return fail(CCD_ERR_ARG, "bad producer mask");

@@ -105,6 +105,9 @@ int ccd_ups_convt(const float *d_in, int c, int h, int w, const float *w1d, int 
 int ccd_syn_layer(const float *d_in, int h, int w, const SynLayerDev &L, float *d_out, cudaStream_t st);
 int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, const SynLayerDev &L1,
                        float *d_out, cudaStream_t st);
+// whole synthesis in one kernel when the architecture allows it (returns -1 otherwise: use the layer kernels)
+int ccd_syn_fused(const float *d_in, int h, int w, int cin, const SynLayerDev *layers, int n_layers,
+                  const SynLayerDev *stab, const SynLayerDev &ot, float *d_out, cudaStream_t st);
 int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st);
 int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st);
 // F.interpolate bilinear (mode 1) / bicubic (mode 2), align_corners=False; sy/sx = 0.5 (scale_factor 2) or in/out

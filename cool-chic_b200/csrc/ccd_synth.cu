@@ -141,6 +141,228 @@ __global__ void k_syn_pw2(const float *__restrict__ in, size_t plane, int cin, i
         if (c < cout) out[(size_t)c * plane + p] = relu1 ? fmaxf(o[c], 0.0f) : o[c];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused synthesis (core/synthesis.py:272-294) for the architecture family every Cool-chic preset uses:
+//   [1x1 cin -> hid (relu?)] [1x1 hid -> C (relu?)] then 0, 1 or 2 3x3 layers C -> C (residual? relu?)
+//   + linear stabiliser (1x1 on the dense input) + output transform (1x1 C -> C).
+// One CTA = one 32 x 16 output tile.  Stage A evaluates the two 1x1 layers on the tile plus a halo of one
+// pixel per 3x3 layer (three positions per thread share each weight fetch), the 3x3 layers go from shared
+// memory to shared memory, the stabiliser / residual adds / output transform happen in registers, and only
+// the final C planes are written: the dense latent is read once and nothing else touches HBM.
+// Replicate padding = every stage evaluates out-of-frame positions at their clamped coordinates.
+// Same fp32 operation order per output as the unfused kernels (and oracle/ccoracle.c::syn_conv), so the
+// result is bit-identical.
+struct SynFusedParams {
+    const float *in;    // dense latent [cin][h][w]
+    float *out;         // [C][h][w]
+    int h, w, cin, hid, n3;            // n3: number of 3x3 layers (0..2)
+    int relu0, relu1, res3[2], relu3[2];
+    int stab_in;                       // 0: no stabiliser
+    const float *w0, *b0, *w1, *b1;    // [hid][cin], [hid], [C][hid], [C]
+    const float *w3[2], *b3[2];        // [C][C][3][3], [C]
+    const float *ws, *bs, *wo, *bo;    // [C][stab_in], [C], [C][C], [C]
+};
+constexpr int SF_TW = 32, SF_TH = 16, SF_THREADS = 256;
+
+template <int CINP, int C>
+__global__ void __launch_bounds__(SF_THREADS) k_syn_fused(SynFusedParams P) {
+    extern __shared__ __align__(16) float sf_smem[];
+    const int n3 = P.n3, hid = P.hid, cin = P.cin;
+    const int RW = SF_TW + 2 * n3, RH = SF_TH + 2 * n3;  // stage-A region
+    // shared memory: weights, then region buffers
+    float *sw0 = sf_smem;                    // [hid][CINP]
+    float *sb0 = sw0 + hid * CINP;           // [hid]
+    float *sw1 = sb0 + hid;                  // [hid][4*ceil(C/4)]  (transposed: one vector load per hidden unit)
+    constexpr int CP = (C + 3) & ~3;
+    float *sb1 = sw1 + hid * CP;             // [CP]
+    float *sw3 = sb1 + CP;                   // [2][C][C][9]
+    float *sb3 = sw3 + 2 * C * C * 9;        // [2][CP]
+    float *sws = sb3 + 2 * CP;               // [C][CINP]
+    float *sbs = sws + C * CINP;             // [CP]
+    float *swo = sbs + CP;                   // [C][CP]
+    float *sbo = swo + C * CP;               // [CP]
+    float *bufA = sbo + CP;                  // [C][RH][RW]
+    float *bufB = bufA + C * RH * RW;        // [C][RH-2][RW-2]   (n3 == 2)
+    float *sstab = bufB + (n3 == 2 ? C * (RH - 2) * (RW - 2) : 0);  // [C][SF_TH][SF_TW]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < hid * CINP; i += SF_THREADS) {
+        const int hh = i / CINP, ci = i - hh * CINP;
+        sw0[i] = ci < cin ? P.w0[hh * cin + ci] : 0.0f;
+    }
+    for (int i = tid; i < hid; i += SF_THREADS) sb0[i] = P.b0[i];
+    for (int i = tid; i < hid * CP; i += SF_THREADS) {
+        const int hh = i / CP, c = i - hh * CP;
+        sw1[i] = c < C ? P.w1[c * hid + hh] : 0.0f;
+    }
+    for (int i = tid; i < CP; i += SF_THREADS) {
+        sb1[i] = i < C ? P.b1[i] : 0.0f;
+        sbs[i] = (i < C && P.stab_in) ? P.bs[i] : 0.0f;
+        sbo[i] = i < C ? P.bo[i] : 0.0f;
+        for (int l = 0; l < 2; l++) sb3[l * CP + i] = (i < C && l < n3) ? P.b3[l][i] : 0.0f;
+    }
+    for (int l = 0; l < n3; l++)
+        for (int i = tid; i < C * C * 9; i += SF_THREADS) sw3[l * C * C * 9 + i] = P.w3[l][i];
+    for (int i = tid; i < C * CINP; i += SF_THREADS) {
+        const int c = i / CINP, ci = i - c * CINP;
+        sws[i] = (ci < P.stab_in) ? P.ws[c * P.stab_in + ci] : 0.0f;
+    }
+    for (int i = tid; i < C * CP; i += SF_THREADS) {
+        const int c = i / CP, k = i - c * CP;
+        swo[i] = k < C ? P.wo[c * C + k] : 0.0f;
+    }
+    __syncthreads();
+
+    const int x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
+    const int H = P.h, W = P.w;
+    const size_t plane = (size_t)H * W;
+    // ---- stage A: two 1x1 layers (+ stabiliser on the tile itself) on RH x RW positions, 3 per thread
+    const int nA = RH * RW;
+    for (int base = 0; base < nA; base += 3 * SF_THREADS) {
+        float x[3][CINP], o[3][C];
+        int pos[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int pp = base + q * SF_THREADS + tid;
+            pos[q] = pp;
+            const int py = pp / RW, px = pp - py * RW;
+            const int gy = clampi(y0 - n3 + py, 0, H - 1), gx = clampi(x0 - n3 + px, 0, W - 1);
+            const float *src = P.in + (size_t)gy * W + gx;
+#pragma unroll
+            for (int ci = 0; ci < CINP; ci++) x[q][ci] = (pp < nA && ci < cin) ? __ldg(src + (size_t)ci * plane) : 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; c++) o[q][c] = sb1[c];
+        }
+        for (int hh = 0; hh < hid; hh++) {
+            float wv[CINP];
+#pragma unroll
+            for (int v = 0; v < CINP / 4; v++) {
+                const float4 t = *reinterpret_cast<const float4 *>(sw0 + hh * CINP + 4 * v);
+                wv[4 * v] = t.x; wv[4 * v + 1] = t.y; wv[4 * v + 2] = t.z; wv[4 * v + 3] = t.w;
+            }
+            float w1v[CP];
+#pragma unroll
+            for (int v = 0; v < CP / 4; v++) {
+                const float4 t = *reinterpret_cast<const float4 *>(sw1 + hh * CP + 4 * v);
+                w1v[4 * v] = t.x; w1v[4 * v + 1] = t.y; w1v[4 * v + 2] = t.z; w1v[4 * v + 3] = t.w;
+            }
+            const float bb = sb0[hh];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float a = bb;
+#pragma unroll
+                for (int ci = 0; ci < CINP; ci++)
+                    if (ci < cin) a = __fmaf_rn(wv[ci], x[q][ci], a);
+                if (P.relu0) a = fmaxf(a, 0.0f);
+#pragma unroll
+                for (int c = 0; c < C; c++) o[q][c] = __fmaf_rn(w1v[c], a, o[q][c]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            if (pos[q] >= nA) continue;
+            const int py = pos[q] / RW, px = pos[q] - py * RW;
+#pragma unroll
+            for (int c = 0; c < C; c++) bufA[(c * RH + py) * RW + px] = P.relu1 ? fmaxf(o[q][c], 0.0f) : o[q][c];
+            // stabiliser (synthesis.py:286-289) for positions of the tile itself
+            const int ty = py - n3, tx = px - n3;
+            if (P.stab_in && ty >= 0 && ty < SF_TH && tx >= 0 && tx < SF_TW) {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float a = sbs[c];
+#pragma unroll
+                    for (int ci = 0; ci < CINP; ci++)
+                        if (ci < P.stab_in) a = __fmaf_rn(sws[c * CINP + ci], x[q][ci], a);
+                    sstab[(c * SF_TH + ty) * SF_TW + tx] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 3x3 layers, shared memory -> shared memory (the last one -> registers -> output)
+    const float *cur = bufA;
+    int cw = RW, chh = RH, off = n3;  // current buffer geometry; off = its halo w.r.t. the tile
+    for (int l = 0; l < n3 - 1; l++) {
+        // intermediate 3x3 layer on the region shrunk by one pixel
+        const int ow = cw - 2, oh = chh - 2;
+        const float *wl = sw3 + l * C * C * 9;
+        for (int pp = tid; pp < ow * oh; pp += SF_THREADS) {
+            const int py = pp / ow, px = pp - py * ow;
+            // this position in frame coordinates, clamped (replicate padding of the NEXT layer), then back
+            // to buffer coordinates of `cur`
+            const int gy = clampi(y0 - (off - 1) + py, 0, H - 1), gx = clampi(x0 - (off - 1) + px, 0, W - 1);
+            const int by = gy - (y0 - off), bx = gx - (x0 - off);
+            float acc[C];
+#pragma unroll
+            for (int co = 0; co < C; co++) acc[co] = sb3[l * CP + co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++)
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        const float v = cur[(ci * chh + by + ky - 1) * cw + bx + kx - 1];
+#pragma unroll
+                        for (int co = 0; co < C; co++) acc[co] = __fmaf_rn(wl[((co * C + ci) * 3 + ky) * 3 + kx], v, acc[co]);
+                    }
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                float a = acc[co];
+                if (P.res3[l]) a = __fadd_rn(a, cur[(co * chh + by) * cw + bx]);
+                if (P.relu3[l]) a = fmaxf(a, 0.0f);
+                bufB[(co * oh + py) * ow + px] = a;
+            }
+        }
+        __syncthreads();
+        cur = bufB;
+        cw = ow;
+        chh = oh;
+        off -= 1;
+    }
+    // ---- last stage on the tile: last 3x3 layer (if any), + stabiliser, output transform, store
+    for (int pp = tid; pp < SF_TW * SF_TH; pp += SF_THREADS) {
+        const int ty = pp / SF_TW, tx = pp - ty * SF_TW;
+        const int gy = y0 + ty, gx = x0 + tx;
+        if (gy >= H || gx >= W) continue;
+        const int by = ty + off, bx = tx + off;
+        float t[C];
+        if (n3 > 0) {
+            const int l = n3 - 1;
+            const float *wl = sw3 + l * C * C * 9;
+#pragma unroll
+            for (int co = 0; co < C; co++) t[co] = sb3[l * CP + co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++)
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        const float v = cur[(ci * chh + by + ky - 1) * cw + bx + kx - 1];
+#pragma unroll
+                        for (int co = 0; co < C; co++) t[co] = __fmaf_rn(wl[((co * C + ci) * 3 + ky) * 3 + kx], v, t[co]);
+                    }
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                if (P.res3[l]) t[co] = __fadd_rn(t[co], cur[(co * chh + by) * cw + bx]);
+                if (P.relu3[l]) t[co] = fmaxf(t[co], 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int co = 0; co < C; co++) t[co] = cur[(co * chh + by) * cw + bx];
+        }
+        if (P.stab_in) {
+#pragma unroll
+            for (int co = 0; co < C; co++) t[co] = __fadd_rn(t[co], sstab[(co * SF_TH + ty) * SF_TW + tx]);
+        }
+#pragma unroll
+        for (int co = 0; co < C; co++) {
+            float a = sbo[co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++) a = __fmaf_rn(swo[co * CP + ci], t[ci], a);
+            P.out[(size_t)co * plane + (size_t)gy * W + gx] = a;
+        }
+    }
+}
+
 __global__ void k_add(float *__restrict__ a, const float *__restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = __fadd_rn(a[i], b[i]);
@@ -315,6 +537,58 @@ int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, c
         d_in, plane, L0.cin, L0.cout, L1.cout, L0.relu, L1.relu, L0.w, L0.b, L1.w, L1.b, d_out);
     g_ccd_launches++;
     return (int)cudaGetLastError();
+}
+
+template <int CINP, int C>
+static int launch_syn_fused(const SynFusedParams &P, cudaStream_t st) {
+    constexpr int CP = (C + 3) & ~3;
+    const int RW = SF_TW + 2 * P.n3, RH = SF_TH + 2 * P.n3;
+    size_t fl = (size_t)P.hid * CINP + P.hid + (size_t)P.hid * CP + CP + 2 * C * C * 9 + 2 * CP + C * CINP + CP + C * CP + CP;
+    fl += (size_t)C * RH * RW + (P.n3 == 2 ? (size_t)C * (RH - 2) * (RW - 2) : 0) + (size_t)C * SF_TH * SF_TW;
+    const size_t smem = fl * sizeof(float);
+    auto kern = k_syn_fused<CINP, C>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const dim3 grid((P.w + SF_TW - 1) / SF_TW, (P.h + SF_TH - 1) / SF_TH, 1);
+    kern<<<grid, SF_THREADS, smem, st>>>(P);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+// returns -1 when the architecture is outside the fused family (caller falls back to the layer kernels)
+int ccd_syn_fused(const float *d_in, int h, int w, int cin, const SynLayerDev *layers, int n_layers,
+                  const SynLayerDev *stab, const SynLayerDev &ot, float *d_out, cudaStream_t st) {
+    if (n_layers < 2 || n_layers > 4) return -1;
+    const SynLayerDev &L0 = layers[0], &L1 = layers[1];
+    const int C = L1.cout;
+    if (L0.k != 1 || L1.k != 1 || L0.residual || L1.residual || cin > 16 || L0.cout > 256 || C < 2 || C > 5) return -1;
+    if (ot.cin != C || ot.cout != C) return -1;
+    for (int l = 2; l < n_layers; l++)
+        if (layers[l].k != 3 || layers[l].cin != C || layers[l].cout != C) return -1;
+    if (stab && (stab->cin > cin || stab->cout != C)) return -1;
+    SynFusedParams P;
+    P.in = d_in; P.out = d_out; P.h = h; P.w = w; P.cin = cin; P.hid = L0.cout; P.n3 = n_layers - 2;
+    P.relu0 = L0.relu; P.relu1 = L1.relu;
+    for (int l = 0; l < 2; l++) {
+        const bool on = l < P.n3;
+        P.res3[l] = on ? layers[2 + l].residual : 0;
+        P.relu3[l] = on ? layers[2 + l].relu : 0;
+        P.w3[l] = on ? layers[2 + l].w : nullptr;
+        P.b3[l] = on ? layers[2 + l].b : nullptr;
+    }
+    P.stab_in = stab ? stab->cin : 0;
+    P.w0 = L0.w; P.b0 = L0.b; P.w1 = L1.w; P.b1 = L1.b;
+    P.ws = stab ? stab->w : nullptr; P.bs = stab ? stab->b : nullptr;
+    P.wo = ot.w; P.bo = ot.b;
+    const int cinp = cin <= 4 ? 4 : (cin <= 8 ? 8 : 16);
+#define SF_CASE(CI, CC) if (cinp == CI && C == CC) return launch_syn_fused<CI, CC>(P, st)
+    SF_CASE(4, 2); SF_CASE(4, 3); SF_CASE(4, 4); SF_CASE(4, 5);
+    SF_CASE(8, 2); SF_CASE(8, 3); SF_CASE(8, 4); SF_CASE(8, 5);
+    SF_CASE(16, 2); SF_CASE(16, 3); SF_CASE(16, 4); SF_CASE(16, 5);
+#undef SF_CASE
+    return -1;
 }
 
 int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st) {

@@ -179,6 +179,9 @@ uint64_t ccd_debug_launch_count(void);
 /* Tuning knob: which of warps 0..14 of the entropy CTA act as ARM producers (bit i = warp i;
  * warp 15 is the range coder).  Default 0x7777: the coder keeps scheduler partition 3. */
 int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask);
+/* 1 (default): one fused kernel for the synthesis when the architecture allows it; 0: one kernel per
+ * layer.  Both give bit-identical results (tests/test_gpu_decode.py). */
+int ccd_debug_set_fused_synthesis(CcdContext *ctx, int on);
 
 /* Entropy-kernel status words of the last job of the last call: [0] error, [1] words consumed,
  * [2] slow-path symbols (outside the 31-symbol window), [3] words emitted (encode modes),

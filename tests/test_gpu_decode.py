@@ -387,3 +387,42 @@ def test_common_randomness_1080p_properties(ctx, seed_stream):
     _, _, c2, nn2, pay2 = synth.parse_single_image(plain)
     p = ctx.decode_coolchic(desc_from_header(c2), nn2, pay2)
     assert float((a - p).abs().mean()) > 1e-3
+
+
+def test_fused_synthesis_equals_layer_kernels(ctx, seed_stream):
+    """The fused synthesis kernel (tile + halo, shared-memory 3x3 stages) against the one-kernel-per-layer
+    path: bit-identical on every architecture of the fused family that the streams use (3 / 4 / 5 / 2 output
+    channels, 0-2 3x3 layers, with and without stabiliser, common randomness), odd sizes and tiny frames."""
+    import torch
+
+    from coolchic_b200 import synth
+    from coolchic_b200._desc import desc_from_header
+
+    cases = [
+        ((131, 203), (0, 6), None, None),                                   # hop, 3 channels, 2 x 3x3
+        ((70, 50), (0, 3), None, synth._syn_overrides(16, 4, 4)),           # P residue: 4 channels
+        ((64, 96), (0, 4), None, synth._syn_overrides(16, 5, 3)),           # B residue: 5 channels, one 3x3
+        ((48, 80), (2, 5), "nearest", synth._syn_overrides(16, 2, 2)),      # motion: 2 channels, no 3x3, resize
+        ((40, 56), (0, 3), None, {"flag_common_randomness": 1}),            # 8 inputs, stabiliser on 4
+        ((17, 9), (0, 2), None, None),                                      # smaller than one tile
+    ]
+    try:
+        for size, lat, fin, ov in cases:
+            cc, h, _ = synth.make_coolchic(ctx, seed_stream, size, lat, None, seed=2, final_upsampling_type=fin, overrides=ov)
+            h2 = type(h)()
+            rest = h2.read_header(cc)
+            d = desc_from_header(h2)
+            nnb = rest[:h2.get_value("nn_n_bytes")]
+            lb = rest[h2.get_value("nn_n_bytes"):][:h2.get_value("n_bytes_latent")]
+            ctx.set_fused_synthesis(True)
+            n0 = ctx.launch_count()
+            a = ctx.decode_coolchic(d, nnb, lb)
+            n_fused = ctx.launch_count() - n0
+            ctx.set_fused_synthesis(False)
+            n0 = ctx.launch_count()
+            b = ctx.decode_coolchic(d, nnb, lb)
+            n_layers = ctx.launch_count() - n0
+            assert torch.equal(a, b), (size, lat)
+            assert n_fused < n_layers, (size, n_fused, n_layers)  # the fused kernel did run
+    finally:
+        ctx.set_fused_synthesis(True)
