@@ -676,10 +676,15 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
         for (int i = 0; i < L.kc_par; i++) par_c[i] = (float)P.nn[(size_t)(L.ups_cw + (int64_t)kid * L.kc_par + i)] * qs_uw;
         expand_sym(par_t, d->ups_k, full_t);
         expand_sym(par_c, d->ups_pre_k, full_c);
-        if ((rc = ccd_ups_pre(d_lat + P.lat_off_by_grid[gt], th, tw, full_c, d->ups_pre_k, nxt, st)))
-            return fail(CCD_ERR_CUDA, "ups_pre launch");
-        if ((rc = ccd_ups_convt(cur, cc, ch, cw, full_t, d->ups_k, nxt + (size_t)th * tw, th, tw, st)))
-            return fail(CCD_ERR_CUDA, "ups_convt launch");
+        if (ctx->fused_synthesis && d->ups_k == 8 && d->ups_pre_k == 7) {
+            if ((rc = ccd_ups_level(d_lat + P.lat_off_by_grid[gt], th, tw, cur, cc, ch, cw, full_t, full_c, nxt, st)))
+                return fail(CCD_ERR_CUDA, "ups_level launch");
+        } else {
+            if ((rc = ccd_ups_pre(d_lat + P.lat_off_by_grid[gt], th, tw, full_c, d->ups_pre_k, nxt, st)))
+                return fail(CCD_ERR_CUDA, "ups_pre launch");
+            if ((rc = ccd_ups_convt(cur, cc, ch, cw, full_t, d->ups_k, nxt + (size_t)th * tw, th, tw, st)))
+                return fail(CCD_ERR_CUDA, "ups_convt launch");
+        }
         std::swap(cur, nxt);
         ch = th;
         cw = tw;

@@ -102,6 +102,10 @@ int ccd_ups_pre(const int8_t *d_lat, int h, int w, const float *w1d, int k, floa
 int ccd_ups_first(const int8_t *d_lat, int h, int w, float *d_out, cudaStream_t st);
 int ccd_ups_convt(const float *d_in, int c, int h, int w, const float *w1d, int k, float *d_out, int ht,
                   int wt, cudaStream_t st);
+// one cascade level in one launch (ups_k == 8, ups_pre_k == 7 only): out[0] = pre-concat conv of the target latent,
+// out[1 + c] = transposed conv of in[c]
+int ccd_ups_level(const int8_t *d_lat, int th, int tw, const float *d_in, int cc, int ch, int cw, const float *wt1d,
+                  const float *wc1d, float *d_out, cudaStream_t st);
 int ccd_syn_layer(const float *d_in, int h, int w, const SynLayerDev &L, float *d_out, cudaStream_t st);
 int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, const SynLayerDev &L1,
                        float *d_out, cudaStream_t st);

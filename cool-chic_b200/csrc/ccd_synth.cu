@@ -76,6 +76,71 @@ __global__ void k_ups_convt(const float *__restrict__ in, int h, int w, K1d kw, 
     out[((size_t)c * ht + u) * wt + v] = acc;
 }
 
+// One level of the upsampling cascade (Upsampling.forward, upsampling.py:463-500) for the default kernel
+// sizes (8-tap transposed conv, 7-tap pre-concatenation conv) in ONE launch: blockIdx.z == 0 filters the
+// target grid's own latent (k_ups_pre), z >= 1 upsamples channel z - 1 of the coarser stack (k_ups_convt).
+// The separable kernels' 2-D products w[a] * w[b] are formed once on the host (one fp32 multiply each, the
+// same value the per-tap __fmul_rn gives); a thread of the transposed part produces a 2 x 2 output block from
+// one 5 x 5 clamped input window (25 loads for 64 FMAs).  Accumulation order per output = k_ups_convt / k_ups_pre.
+struct UpsLevelParams {
+    const int8_t *lat;  // target grid [th][tw]
+    const float *in;    // coarser stack [cc][ch][cw]
+    float *out;         // [cc + 1][th][tw]
+    int cc, ch, cw, th, tw;
+    float kt[8][8];     // transposed-conv taps
+    float kc[7][7];     // pre-concatenation taps
+};
+__global__ void __launch_bounds__(256) k_ups_level(UpsLevelParams P) {
+    const int th = P.th, tw = P.tw;
+    if (blockIdx.z == 0) {
+        const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+        if (x >= tw || y >= th) return;
+        float acc = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            const int yy = y + a - 3;
+#pragma unroll
+            for (int b = 0; b < 7; b++) {
+                const int xx = x + b - 3;
+                if (yy >= 0 && yy < th && xx >= 0 && xx < tw) acc = __fmaf_rn(P.kc[a][b], (float)P.lat[(size_t)yy * tw + xx], acc);
+            }
+        }
+        P.out[(size_t)y * tw + x] = __fadd_rn(acc, (float)P.lat[(size_t)y * tw + x]);
+        return;
+    }
+    // transposed part: output block (2q .. 2q+1, 2s .. 2s+1)
+    const int s0 = blockIdx.x * 32 + threadIdx.x, q = blockIdx.y * 8 + threadIdx.y;
+    if (2 * s0 >= tw || 2 * q >= th) return;
+    const int c = blockIdx.z - 1, h = P.ch, w = P.cw;
+    const float *src = P.in + (size_t)c * h * w;
+    float win[5][5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const float *row = src + (size_t)clampi(q - 2 + i, 0, h - 1) * w;
+#pragma unroll
+        for (int j = 0; j < 5; j++) win[i][j] = __ldg(row + clampi(s0 - 2 + j, 0, w - 1));
+    }
+    float *dst = P.out + (size_t)(c + 1) * th * tw;
+#pragma unroll
+    for (int du = 0; du < 2; du++) {
+        const int u = 2 * q + du;
+        if (u >= th) continue;
+#pragma unroll
+        for (int dv = 0; dv < 2; dv++) {
+            const int v = 2 * s0 + dv;
+            if (v >= tw) continue;
+            // u = 2q: input rows q-2 .. q+1 with taps a = 7, 5, 3, 1;  u = 2q+1: rows q-1 .. q+2, a = 6, 4, 2, 0
+            float acc = 0.0f;
+#pragma unroll
+            for (int t1 = 0; t1 < 4; t1++)
+#pragma unroll
+                for (int t2 = 0; t2 < 4; t2++)
+                    acc = __fmaf_rn(P.kt[(1 - du) + 6 - 2 * t1][(1 - dv) + 6 - 2 * t2], win[t1 + du][t2 + dv], acc);
+            dst[(size_t)u * tw + v] = acc;
+        }
+    }
+}
+
 // generic SynthesisConv2d: one thread = one pixel, loops over output channels
 __global__ void k_syn_layer(const float *__restrict__ in, int h, int w, int cin, int cout, int k, int residual,
                             int relu, const float *__restrict__ wt, const float *__restrict__ bias,
@@ -517,6 +582,25 @@ int ccd_ups_pre(const int8_t *d_lat, int h, int w, const float *w1d, int k, floa
 int ccd_ups_convt(const float *d_in, int c, int h, int w, const float *w1d, int k, float *d_out, int ht,
                   int wt, cudaStream_t st) {
     k_ups_convt<<<grid2(wt, ht, c), kBlock2, 0, st>>>(d_in, h, w, make_k1d(w1d, k), k, d_out, ht, wt);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+int ccd_ups_level(const int8_t *d_lat, int th, int tw, const float *d_in, int cc, int ch, int cw, const float *wt1d,
+                  const float *wc1d, float *d_out, cudaStream_t st) {
+    UpsLevelParams P;
+    P.lat = d_lat; P.in = d_in; P.out = d_out; P.cc = cc; P.ch = ch; P.cw = cw; P.th = th; P.tw = tw;
+    for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 8; b++) {
+            volatile float k = wt1d[a] * wt1d[b];  // one rounded fp32 product, no contraction
+            P.kt[a][b] = k;
+        }
+    for (int a = 0; a < 7; a++)
+        for (int b = 0; b < 7; b++) {
+            volatile float k = wc1d[a] * wc1d[b];
+            P.kc[a][b] = k;
+        }
+    k_ups_level<<<grid2(tw, th, cc + 1), kBlock2, 0, st>>>(P);
     g_ccd_launches++;
     return (int)cudaGetLastError();
 }
