@@ -81,13 +81,57 @@ def decode_frame(bitstream_bytes: bytes, reference_frames: List[FrameData], verb
     return frame, rest
 
 
+def output_shape(header: CoolChicHeader) -> Tuple[int, int, int, int]:
+    """Shape of a Cool-chic's raw output [1, C, H, W] from its header alone (what the ranks that did not
+    decode it allocate before the broadcast)."""
+    p = header.get_coolchic_parameter()
+    c = int(p.layers_synthesis[-1].split("-")[0])
+    return (1, c, int(p.img_size[0]), int(p.img_size[1]))
+
+
+def _decode_all_coolchics(parsed, device: int, decode_fn=None) -> List[Dict[str, torch.Tensor]]:
+    """Pass 1 of decode_video: every Cool-chic of every frame.  Single process: one concurrent batch.
+    Under torch.distributed (SURVEY 8e / BASELINE configs[4]): Cool-chic i of the flattened list is decoded by
+    rank i mod world, then broadcast from its owner, so every rank holds every raw output and
+    reconstructs the GOP itself (the reconstruction is a few elementwise kernels)."""
+    import torch.distributed as dist
+
+    from ..dist import shard_indices
+
+    decode_fn = decode_fn or decode_coolchics
+    flat = [(i, name) for i, (_, ccs) in enumerate(parsed) for name in ccs]
+    hdr = [parsed[i][1][n][0] for i, n in flat]
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    mine = shard_indices(len(flat), rank, world)
+    outs_mine = decode_fn([hdr[k] for k in mine], [parsed[flat[k][0]][1][flat[k][1]][1] for k in mine],
+                          [parsed[flat[k][0]][1][flat[k][1]][2] for k in mine], device=device)
+    outs: List[Optional[torch.Tensor]] = [None] * len(flat)
+    for k, o in zip(mine, outs_mine):
+        outs[k] = o
+    if world > 1:
+        ref = outs_mine[0] if outs_mine else None
+        for k in range(len(flat)):
+            owner = k % world
+            if outs[k] is None:
+                dev = ref.device if ref is not None else (torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu"))
+                outs[k] = torch.empty(output_shape(hdr[k]), dtype=torch.float32, device=dev)
+            dist.broadcast(outs[k], src=owner)
+    cc_out: List[Dict[str, torch.Tensor]] = [dict() for _ in parsed]
+    for (i, name), o in zip(flat, outs):
+        cc_out[i][name] = o
+    return cc_out
+
+
 @torch.no_grad()
-def decode_video(bitstream_path: str, decoded_path: Optional[str] = None, max_decoding_order: int = -1,
-                 verbosity: int = 0, device: int = 0, output_device: str = "cpu") -> Dict[str, FrameData]:
-    """Decode an image or video bitstream; optionally save the frames (PNG / PPM / YUV by
-    extension).  Returns ``{str(display_index): FrameData}``."""
-    with open(bitstream_path, "rb") as f_in:
-        bitstream_bytes = f_in.read()
+def decode_video_bytes(bitstream_bytes: bytes, decoded_path: Optional[str] = None, max_decoding_order: int = -1,
+                       verbosity: int = 0, device: int = 0, output_device: str = "cpu", decode_fn=None,
+                       reconstruct_fn=None) -> Dict[str, FrameData]:
+    """decode_video on bytes already in memory.  With an initialised torch.distributed process group every
+    rank must call it with the same bytes (see dist.broadcast_byte_strings): the Cool-chics are sharded over
+    the ranks, every rank returns all frames.  ``decode_fn`` / ``reconstruct_fn`` exist for the CPU (gloo)
+    test of the plumbing."""
+    reconstruct_fn = reconstruct_fn or _reconstruct
     video_header = VideoHeader()
     bitstream_bytes = video_header.read_header(bitstream_bytes)
     coding_structure = video_header.get_coding_structure()
@@ -97,18 +141,13 @@ def decode_video(bitstream_path: str, decoded_path: Optional[str] = None, max_de
     if max_decoding_order == -1:
         max_decoding_order = coding_structure.get_max_coding_order()
 
-    # ---- pass 1: parse every frame, decode ALL Cool-chics concurrently on the device
+    # ---- pass 1: parse every frame, decode ALL Cool-chics concurrently on the device(s)
     t0 = time.time()
     parsed = []
     for coding_idx in range(max_decoding_order + 1):
         frame_header, ccs, bitstream_bytes = _parse_frame(bitstream_bytes)
         parsed.append((frame_header, ccs))
-    flat = [(i, name) for i, (_, ccs) in enumerate(parsed) for name in ccs]
-    outs = decode_coolchics([parsed[i][1][n][0] for i, n in flat], [parsed[i][1][n][1] for i, n in flat],
-                            [parsed[i][1][n][2] for i, n in flat], device=device)
-    cc_out = [dict() for _ in parsed]
-    for (i, name), o in zip(flat, outs):
-        cc_out[i][name] = o
+    cc_out = _decode_all_coolchics(parsed, device, decode_fn)
     t_cc = (time.time() - t0) / max(1, len(parsed))
 
     # ---- pass 2: reconstruct in coding order (references looked up by display index)
@@ -120,9 +159,10 @@ def decode_video(bitstream_path: str, decoded_path: Optional[str] = None, max_de
             for n in ccs:
                 print(ccs[n][0].pretty_string())
         refs_data = [coding_structure.get_frame_from_display_order(idx_ref).data for idx_ref in frame.index_references]
-        frame.set_frame_data(_reconstruct(frame_header, cc_out[coding_idx], refs_data, device))
+        frame.set_frame_data(reconstruct_fn(frame_header, cc_out[coding_idx], refs_data, device))
         cc_out[coding_idx] = None
-        torch.cuda.synchronize(device)
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(device)
         print(f"Decoding frame {frame.display_order:<4} time = {time.time() - start_time + t_cc:6.2f} seconds.")
 
     all_frames = {}
@@ -135,3 +175,12 @@ def decode_video(bitstream_path: str, decoded_path: Optional[str] = None, max_de
         if decoded_path is not None:
             save_frame_data_to_file(data, decoded_path, append=display_idx != 0)
     return all_frames
+
+
+def decode_video(bitstream_path: str, decoded_path: Optional[str] = None, max_decoding_order: int = -1,
+                 verbosity: int = 0, device: int = 0, output_device: str = "cpu") -> Dict[str, FrameData]:
+    """Decode an image or video bitstream; optionally save the frames (PNG / PPM / YUV by
+    extension).  Returns ``{str(display_index): FrameData}``."""
+    with open(bitstream_path, "rb") as f_in:
+        bitstream_bytes = f_in.read()
+    return decode_video_bytes(bitstream_bytes, decoded_path, max_decoding_order, verbosity, device, output_device)
