@@ -764,12 +764,14 @@ __device__ __noinline__ SlowOut coder_slow(uint32_t res_a, uint32_t win_a, uint3
     const uint64_t scale = R >> 24;
     const uint64_t lo = scale * h.x, rn = scale * h.y;
     const uint64_t hiM = lo + rn;  // = scale * left(M + 1)
-    const uint64_t p1 = scale * h.z, q2 = scale * h.w;
+    // which neighbour can it be?  D < lo: only the left one (needs left(M-1)), else only the right one (left(M+2))
     const bool is_m = (D - lo) < rn;
-    const bool is_l = (p1 <= D) & (D < lo);
-    const bool is_r = (hiM <= D) & (D < q2);
-    uint64_t nlo = is_m ? lo : (is_l ? p1 : hiM);
-    uint64_t nhi = is_m ? hiM : (is_l ? lo : q2);
+    const bool below = D < lo;
+    const uint64_t pn = scale * (below ? h.z : h.w);
+    const bool is_l = below & (pn <= D);
+    const bool is_r = (!below) & (hiM <= D) & (D < pn);
+    uint64_t nlo = is_m ? lo : (is_l ? pn : hiM);
+    uint64_t nhi = is_m ? hiM : (is_l ? lo : pn);
     uint32_t rw = res_tag(j) | (is_l ? (M - 1u) : (M + 1u));
     const uint32_t slot = j & ring_mask;
     uint32_t flags = is_m ? 0u : 8u;
@@ -923,18 +925,15 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             } while ((int32_t)(limit - j) <= 0);
             PROF_ADD(pc.wait, t0);
         }
-        if ((int32_t)(limit - j) >= 9) {
-            // steady state, six symbols per round trip through the loop: the hot entries of the next triple
+        if ((int32_t)(limit - j) >= 3) {
+            // at least a triple is ready.  Steady state (9 or more ready): six symbols per round trip through
+            // the loop: the hot entries of the next triple
             // are requested while a triple is decoded, and the two register sets swap roles (no copies);
             // the ring's first entries are mirrored behind its end, so one address serves a triple
             uint32_t o = sm.hot + (j & ring_mask) * 16u;
             uint4 a0 = lds_v4(o), a1 = lds_v4(o + 16u), a2 = lds_v4(o + 32u);
             CODER_PRE(a0);
-            while (true) {
-                if ((int32_t)(limit - j) < 9) {
-                    refresh();
-                    if ((int32_t)(limit - j) < 9) break;
-                }
+            while ((int32_t)(limit - j) >= 9) {
                 o = sm.hot + ((j + 3u) & ring_mask) * 16u;
                 const uint4 b0 = lds_v4(o), b1 = lds_v4(o + 16u), b2 = lds_v4(o + 32u);
                 CODER_STEP_SPEC(j, a0, a1);
@@ -953,6 +952,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
 #ifdef CCD_PROFILE
                 pc.seg[3] += 6;
 #endif
+                if ((int32_t)(limit - j) < 9) refresh();
             }
             // a0..a2 are valid (limit - j >= 3 here), lo / rn belong to a0
             CODER_STEP_SPEC(j, a0, a1);
