@@ -307,7 +307,11 @@ def main():
         ent_s = ent_avg / 1e3
         roof = {"bound": "hbm", "kernel": "k_entropy (wavefront ARM + range decoder, one persistent CTA per stream)",
                 "achieved": alg_bytes / ent_s / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": alg_bytes / ent_s / 1e9 / peak, "traffic": None,
+                "frac": alg_bytes / ent_s / 1e9 / peak,
+                # DRAM bytes per launch of this kernel from the committed ncu --set full capture of this command
+                # (profiles/r01_final_ncu_full_summary.csv: 15.3 MB read -- the cumulative-table rows that miss L2 --
+                # and 0 written: the 2.76 MB of latents stay in L2); only quoted for the default workload
+                "traffic": 15306496 if args.workload == "1080p_rgb_7grids" else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ent_avg, "share_of_step": ent_avg / dev_ms,
                 "ns_per_symbol": ent_avg * 1e6 / n_sym, "symbols": n_sym,
                 "note": "serial-latency-bound kernel (one range-coded stream = one dependency chain): "
