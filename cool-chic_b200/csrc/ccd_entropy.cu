@@ -94,22 +94,11 @@ __global__ void k_laplace_domain(const float *__restrict__ scale, int sc_lo, int
     hi[idx] = (n == 0) ? laplace_nonleaky(0.0, b) : laplace_nonleaky(d, b);
 }
 
-__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
-    return *reinterpret_cast<const volatile uint32_t *>(p);
-}
-__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
-    *reinterpret_cast<volatile uint32_t *>(p) = v;
-}
 __device__ __forceinline__ uint64_t splitmix64(uint64_t &s) {
     uint64_t z = (s += 0x9E3779B97F4A7C15ull);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
-}
-__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
-    uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
-    uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
-    return ((uint64_t)hi << 32) | lo;
 }
 
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
@@ -173,7 +162,6 @@ struct SmemLayout {
     uint32_t win;          // shared address: u32 [ring][32]: left(s_lo + t), t = 0..31 (mode at t = 15)
     uint32_t hot;          // shared address: uint4 [ring]: left(M), left(M+1)-left(M), left(M-1), left(M+2), M = mode
     uint32_t res;          // shared address: u32 [ring]: result word of each symbol that is NOT the mode (coder -> helper)
-    uint32_t bc;           // shared address: 16 B broadcast line of the coder warp (new D, R)
     uint32_t rows;         // shared address: int8 [rows][64]
 };
 
@@ -193,8 +181,7 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int r
     p += align16((size_t)arm_bytes);
     L.ifce = base + p;
     p += align16((size_t)ifce_bytes);
-    L.bc = base_a + (uint32_t)p;
-    p += 16;
+    p += 16;  // (spare line)
     L.meta = base_a + (uint32_t)p;
     p += (size_t)ring * 16;
     L.win = base_a + (uint32_t)p;
