@@ -3,7 +3,7 @@ import os
 
 import numpy as np
 import pytest
-from conftest import REFERENCE, has_reference
+from conftest import GOLDEN, REFERENCE, has_reference
 
 
 def test_kodim14_headers(kodim14):
@@ -175,3 +175,24 @@ def test_synthetic_header_and_nn_layout(kodim14, oracle):
         assert len(nn2) == oracle.nn_counts(d2)[0]
     h = synth.make_coolchic_header(kodim14["header"], (512, 768), (0, 6), (4, 6))
     assert np.array_equal(synth.adapt_nn(d, nn, desc_from_header(h)), nn)
+
+
+def test_output_shape_from_header_alone():
+    """decode.output_shape (used by ranks that did not decode a Cool-chic to allocate the broadcast buffer)
+    against the channel counts / sizes of the committed GOP fixture: I residue 3, P residue 4, B residue 5,
+    P motion 2, B motion 4 channels, all at frame size."""
+    from coolchic_b200.bitstream import decode as dec
+
+    data = open(os.path.join(GOLDEN, "gop5_64x96_yuv420.cool"), "rb").read()
+    from coolchic_b200.bitstream.header import VideoHeader
+
+    v = VideoHeader()
+    rest = v.read_header(data)
+    seen = {}
+    for _ in range(5):
+        fh, ccs, rest = dec._parse_frame(rest)
+        for name, (h, _, _) in ccs.items():
+            shp = dec.output_shape(h)
+            assert shp[0] == 1 and shp[2:] == (64, 96)
+            seen[(fh.get_value("frame_type"), name)] = shp[1]
+    assert seen == {("I", "residue"): 3, ("P", "residue"): 4, ("P", "motion"): 2, ("B", "residue"): 5, ("B", "motion"): 4}
