@@ -426,3 +426,40 @@ def test_fused_synthesis_equals_layer_kernels(ctx, seed_stream):
             assert n_fused < n_layers, (size, n_fused, n_layers)  # the fused kernel did run
     finally:
         ctx.set_fused_synthesis(True)
+
+
+def test_corrupt_streams_fail_cleanly_on_the_device(ctx, seed_stream):
+    """Fuzz on the device: bit flips in the NN payload and in the range-coded payload of a small stream.  Every
+    decode returns -- an image (garbage is fine) or a CcdError -- and the context keeps working afterwards."""
+    import random
+
+    import torch
+
+    from coolchic_b200 import _native, synth
+    from coolchic_b200._desc import desc_from_header
+
+    cc, h, _ = synth.make_coolchic(ctx, seed_stream, (96, 160), (0, 4), None, seed=9)
+    h2 = type(h)()
+    rest = h2.read_header(cc)
+    d = desc_from_header(h2)
+    n_nn, n_lat = h2.get_value("nn_n_bytes"), h2.get_value("n_bytes_latent")
+    nnb, lb = rest[:n_nn], rest[n_nn:n_nn + n_lat]
+    good = ctx.decode_coolchic(d, nnb, lb)
+    rng = random.Random(3)
+    n_err = n_ok = 0
+    for trial in range(24):
+        a, b = bytearray(nnb), bytearray(lb)
+        tgt = a if trial % 3 == 0 else b
+        for _ in range(rng.randint(1, 6)):
+            tgt[rng.randrange(len(tgt))] ^= 1 << rng.randrange(8)
+        if trial % 5 == 4:
+            b = b[: rng.randrange(1, len(b))]  # truncated payload: missing words read as zero
+        try:
+            out = ctx.decode_coolchic(d, bytes(a), bytes(b))
+            assert out.shape == good.shape
+            n_ok += 1
+        except _native.CcdError as e:
+            assert e.code in (-1, -2, -3, -4)
+            n_err += 1
+    assert n_ok + n_err == 24
+    assert torch.equal(ctx.decode_coolchic(d, nnb, lb), good)  # the context is still healthy

@@ -196,3 +196,47 @@ def test_output_shape_from_header_alone():
             assert shp[0] == 1 and shp[2:] == (64, 96)
             seen[(fh.get_value("frame_type"), name)] = shp[1]
     assert seen == {("I", "residue"): 3, ("P", "residue"): 4, ("P", "motion"): 2, ("B", "residue"): 5, ("B", "motion"): 4}
+
+
+def test_corrupt_headers_and_payloads_never_crash():
+    """Fuzz: random byte flips in the header / NN-payload region of a real stream.  The host parser either
+    raises a Python exception or yields a description that the C-ABI accepts or rejects with an error code --
+    never a crash, never a silent out-of-range descriptor (ccd_nn_count / ccd_latent_count validate it)."""
+    import ctypes
+    import random
+
+    import numpy as np
+
+    from coolchic_b200 import _native
+    from coolchic_b200._desc import desc_from_header
+    from coolchic_b200.bitstream.header import CoolChicHeader, FrameHeader, VideoHeader
+
+    data = open(os.path.join(GOLDEN, "kodim14.cool"), "rb").read()
+    lib = _native.load_library()
+    rng = random.Random(7)
+    outcomes = {"parse_error": 0, "rejected": 0, "nn_error": 0, "accepted": 0}
+    for trial in range(300):
+        b = bytearray(data[:4096])
+        for _ in range(rng.randint(1, 4)):
+            b[rng.randrange(0, 64 if trial % 2 else 2048)] ^= 1 << rng.randrange(8)
+        try:
+            rest = VideoHeader().read_header(bytes(b))
+            rest = FrameHeader().read_header(rest)
+            c = CoolChicHeader()
+            rest = c.read_header(rest)
+            d = desc_from_header(c)
+        except Exception:
+            outcomes["parse_error"] += 1
+            continue
+        n = lib.ccd_nn_count(ctypes.byref(d))
+        if n < 0 or _native.latent_layout(d)[0] < 0:
+            outcomes["rejected"] += 1
+            continue
+        try:
+            ints = _native.decode_nn(d, rest[: max(0, c.get_value("nn_n_bytes"))])
+            assert len(ints) == n and np.abs(ints).max() < 2**40
+            outcomes["accepted"] += 1
+        except _native.CcdError as e:
+            assert e.code in (-1, -2, -4)
+            outcomes["nn_error"] += 1
+    assert sum(outcomes.values()) == 300 and outcomes["accepted"] > 0 and outcomes["parse_error"] + outcomes["rejected"] + outcomes["nn_error"] > 0
