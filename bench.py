@@ -226,7 +226,9 @@ def main():
     # ---- inputs: rank 0 fabricates one stream per rank, NCCL broadcast of the bytes
     if rank == 0:
         seed_stream = synth.SeedStream(ctx)
-        streams = [synth.make_image_stream(ctx, seed_stream, H, W, fmt, 8, lat_res, hyp_res, seed=r) for r in range(world)]
+        # weak scaling = the same work on every rank: every rank gets (its own broadcast copy of) the same frame
+        one = synth.make_image_stream(ctx, seed_stream, H, W, fmt, 8, lat_res, hyp_res, seed=0)
+        streams = [one for _ in range(world)]
     else:
         streams = None
     if world > 1:
