@@ -132,6 +132,7 @@ def decode_video_bytes(bitstream_bytes: bytes, decoded_path: Optional[str] = Non
     the ranks, every rank returns all frames.  ``decode_fn`` / ``reconstruct_fn`` exist for the CPU (gloo)
     test of the plumbing."""
     reconstruct_fn = reconstruct_fn or _reconstruct
+    bitstream_bytes = memoryview(bitstream_bytes)  # every "remaining bytes" below is a view, not a copy
     video_header = VideoHeader()
     bitstream_bytes = video_header.read_header(bitstream_bytes)
     coding_structure = video_header.get_coding_structure()

@@ -46,9 +46,14 @@ EXP_GOL_TABLE = tuple(range(0, 13))
 class BitReader:
     """MSB-first bit reader over a bytes object."""
 
-    def __init__(self, data: bytes):
-        self._v = int.from_bytes(data, "big")
-        self._n = 8 * len(data)
+    # a header is at most 65 535 bytes (n_bytes_header is a 16-bit field): never turn the whole remaining
+    # bitstream (tens of MB for a GOP) into one Python integer
+    MAX_BYTES = 65536 + 16
+
+    def __init__(self, data):
+        head = data[: self.MAX_BYTES]
+        self._v = int.from_bytes(head, "big")
+        self._n = 8 * len(head)
         self.pos = 0
 
     def read(self, n_bits: int, signed: bool = False) -> int:

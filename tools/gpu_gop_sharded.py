@@ -32,6 +32,25 @@ def digest(frames):
     return h.hexdigest()
 
 
+def install_timers(acc):
+    """wall-clock split of decode_video_bytes: pass 1 (all Cool-chics) vs per-frame reconstruction"""
+    from coolchic_b200.bitstream import decode as dec
+
+    orig_all, orig_rec = dec._decode_all_coolchics, dec._reconstruct
+
+    def timed_all(*a, **k):
+        torch.cuda.synchronize(); t = time.perf_counter(); r = orig_all(*a, **k); torch.cuda.synchronize()
+        acc["pass1_wall_s"] = time.perf_counter() - t
+        return r
+
+    def timed_rec(*a, **k):
+        torch.cuda.synchronize(); t = time.perf_counter(); r = orig_rec(*a, **k); torch.cuda.synchronize()
+        acc["pass2_wall_s"] = acc.get("pass2_wall_s", 0.0) + time.perf_counter() - t
+        return r
+
+    dec._decode_all_coolchics, dec._reconstruct = timed_all, timed_rec
+
+
 def main():
     n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -45,10 +64,13 @@ def main():
         with contextlib.redirect_stdout(io.StringIO()):
             decode_video_bytes(data, device=local, output_device="cuda")  # warm-up (allocations, table build)
             torch.cuda.synchronize()
+            acc = {}
+            install_timers(acc)
             t0 = time.perf_counter()
             frames = decode_video_bytes(data, device=local, output_device="cuda")
             torch.cuda.synchronize()
             t_single = time.perf_counter() - t0
+            sys.stderr.write("split " + json.dumps(acc) + "\n")
         want = digest(frames)
     import torch.distributed as dist
 
@@ -73,6 +95,8 @@ def main():
     else:
         allg = [got]
     if rank == 0:
+        tm = ctx.last_timing()
+        print(json.dumps({"pass1_entropy_ms": tm["entropy_ms"], "pass1_synthesis_ms": tm["synthesis_ms"], "pass1_upload_ms": tm["upload_ms"]}))
         print(json.dumps({"frames": n_frames, "bytes": len(data), "world": world, "all_ranks_equal_single_process": all(g == want for g in allg),
                           "single_gpu_s": t_single, "sharded_s": t_sharded,
                           "single_gpu_mpixel_s": n_frames * H * W / t_single / 1e6, "sharded_mpixel_s": n_frames * H * W / t_sharded / 1e6}))
