@@ -409,6 +409,10 @@ struct CcdContext {
     uint64_t last_upload_bytes = 0;
     uint32_t prod_mask = 0x3777u;  // warps 3, 7, 11 stay idle: the coder warp (15) owns its scheduler
     int fused_synthesis = 1;       // 0: layer-by-layer kernels (ccd_debug_set_fused_synthesis, tests compare both)
+    // entropy launches of different ARM architectures (e.g. intra / residue / motion streams of a GOP) run
+    // side by side on these streams: each launch only fills as many SMs as it has streams
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -862,6 +866,10 @@ void ccd_destroy(CcdContext *c) {
     if (c->h_pin) cudaFreeHost(c->h_pin);
     for (int i = 0; i < 4; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 3; i++) {
+        if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
     delete c;
 }
 
@@ -980,7 +988,7 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
     CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
 
     if (stages & 1) {
-        int t = 0;
+        int t = 0, g = 0;
         while (t < n_jobs) {
             int u = t;
             size_t smem = 0;
@@ -990,10 +998,27 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
             }
             const PreparedJob &J0 = P[(size_t)order[(size_t)t]];
             EntLaunchCfg cfg{J0.d->n_ctx, J0.d->flag_ifce ? J0.d->n_ifce_out : 0, J0.fast, smem};
+            // group 0 on the caller's stream, the next ones on auxiliary streams forked after the upload
+            cudaStream_t sg = st;
+            if (g > 0) {
+                const int a = (g - 1) % 3;
+                if (!ctx->aux[a]) {
+                    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[a], cudaStreamNonBlocking));
+                    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join[a], cudaEventDisableTiming));
+                }
+                sg = ctx->aux[a];
+                CUDA_TRY(cudaStreamWaitEvent(sg, ctx->ev[1], 0));  // the upload (recorded on st before any launch)
+            }
             int e = ccd_entropy_launch(reinterpret_cast<const EntStream *>(dv + off_streams) + t, u - t, cfg, ctx->d_cdf,
-                                       ctx->d_scale, st);
+                                       ctx->d_scale, sg);
             if (e != 0) return fail(CCD_ERR_CUDA, "entropy kernel launch failed: %s", cudaGetErrorString((cudaError_t)e));
+            if (g > 0) {
+                const int a = (g - 1) % 3;
+                CUDA_TRY(cudaEventRecord(ctx->ev_join[a], sg));
+                CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join[a], 0));
+            }
             t = u;
+            g++;
         }
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
