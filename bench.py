@@ -332,10 +332,17 @@ def main():
                         "h2d_bytes_per_step": int(up_bytes), "d2h_bytes_per_step": int(pinned_out.numel() * 4)},
                 "gpu_launches": int(launches), "roofline": roof, "roofline_synthesis": roof_syn,
                 "clocks": clocks.summary()}
+        # informational extras must never cost the headline line
         if not args.no_many_streams and world == 1:
-            line["many_streams"] = many_streams(ctx, synth)
+            try:
+                line["many_streams"] = many_streams(ctx, synth)
+            except Exception as e:  # noqa: BLE001
+                line["many_streams"] = {"error": str(e)[:200]}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(data, n_pixels, 1)
+            try:
+                line["cpu_baseline"] = cpu_baseline(data, n_pixels, 1)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": str(e)[:200], "kind": "port", "cores": 1}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
