@@ -30,7 +30,11 @@ CONFIGS = {
     "img_48x72_rgb_common_randomness": (48, 72, "rgb", (0, 3), None, {"flag_common_randomness": 1}),
     "img_50x70_rgb_final_bicubic": (50, 70, "rgb", (1, 4), "bicubic", None),
     "img_44x60_yuv420_final_bilinear": (44, 60, "yuv420", (2, 5), "bilinear", None),
+    # other ARM shapes (the all-int64 kernel on the device) and a 10-bit 4:4:4 frame
+    "img_48x64_rgb_arm8_1hidden": (48, 64, "rgb", (0, 4), None, {"spatial_context_arm": 8, "n_hidden_layers_arm": 1}),
+    "img_40x56_yuv444_10bit_arm24": (40, 56, "yuv444", (0, 3), None, {"spatial_context_arm": 24}),
 }
+BITDEPTH = {"img_40x56_yuv444_10bit_arm24": 10}
 
 
 def main():
@@ -39,7 +43,9 @@ def main():
     be = pipeline.OracleBackend()
     ss = synth.SeedStream(be)
     for name, (h, w, fmt, lat, fin, ov) in CONFIGS.items():
-        data = synth.make_image_stream(be, ss, h, w, fmt, 8, lat, None, seed=3, final_upsampling_type=fin, overrides=ov)
+        bd = BITDEPTH.get(name, 8)
+        M = 2**bd - 1
+        data = synth.make_image_stream(be, ss, h, w, fmt, bd, lat, None, seed=3, final_upsampling_type=fin, overrides=ov)
         path = os.path.join(GOLD, name + ".cool")
         with open(path, "wb") as f:
             f.write(data)
@@ -47,14 +53,14 @@ def main():
         out = {}
         if fmt == "yuv420":
             for c in "yuv":
-                out[c] = torch.round(fd.data[c][0, 0] * 255).to(torch.int32).numpy().astype(np.uint8)
+                out[c] = torch.round(fd.data[c][0, 0] * M).to(torch.int32).numpy().astype(np.uint16)
         else:
-            out["rgb"] = torch.round(fd.data[0] * 255).to(torch.int32).numpy().astype(np.uint8)
+            out["rgb"] = torch.round(fd.data[0] * M).to(torch.int32).numpy().astype(np.uint16)
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
         _, _, d = pipeline.decode_video(data)[0]
         nbad = ntot = worst = 0
         for k, b in out.items():
-            a = np.round((d[k] if fmt == "yuv420" else d) * 255).astype(np.int32)
+            a = np.round((d[k] if fmt == "yuv420" else d) * M).astype(np.int32)
             worst = max(worst, int(np.abs(a - b.astype(np.int32)).max()))
             nbad += int((a != b).sum())
             ntot += a.size
