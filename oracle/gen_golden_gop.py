@@ -32,7 +32,9 @@ def main():
     # (name, (h, w, frames, format, bitdepth, warp_filter_size)); 2 / 4 = torch grid_sample bilinear / bicubic
     configs = [("gop5_64x96_yuv420", (64, 96, 5, "yuv420", 8, 8)), ("gop3_40x56_rgb", (40, 56, 3, "rgb", 8, 8)),
                ("gop3_48x72_yuv420_bilinear", (48, 72, 3, "yuv420", 8, 2)),
-               ("gop3_40x56_rgb_bicubic", (40, 56, 3, "rgb", 8, 4))]
+               ("gop3_40x56_rgb_bicubic", (40, 56, 3, "rgb", 8, 4)),
+               ("gop3_48x72_yuv420_sinc6", (48, 72, 3, "yuv420", 8, 6)),
+               ("gop4_40x56_rgb_sinc12", (40, 56, 4, "rgb", 8, 12))]
     for name, (h, w, n, fmt, bd, fs) in configs:
         data = synth.make_video_stream(be, ss, h, w, n, fmt, bd, fs, seed=1)
         path = os.path.join(GOLD, name + ".cool")

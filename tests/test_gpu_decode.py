@@ -284,7 +284,8 @@ def test_unsupported_warp_is_an_error_not_a_fallback(ctx):
 
 
 @pytest.mark.parametrize("name,fmt", [("gop5_64x96_yuv420", "yuv420"), ("gop3_40x56_rgb", "rgb"),
-                                      ("gop3_48x72_yuv420_bilinear", "yuv420"), ("gop3_40x56_rgb_bicubic", "rgb")])
+                                      ("gop3_48x72_yuv420_bilinear", "yuv420"), ("gop3_40x56_rgb_bicubic", "rgb"),
+                                      ("gop3_48x72_yuv420_sinc6", "yuv420"), ("gop4_40x56_rgb_sinc12", "rgb")])
 def test_gop_decode_video(ctx, name, fmt, tmp_path):
     """decode_video on a P/B stream against frames decoded by the UNMODIFIED reference."""
     from coolchic_b200.bitstream.decode import decode_video
