@@ -27,7 +27,8 @@ ERROR_NAMES = {
 EXPORTS = [
     "ccd_version", "ccd_sizeof_desc", "ccd_last_error", "ccd_create", "ccd_destroy", "ccd_nn_count",
     "ccd_latent_count", "ccd_decode_nn", "ccd_decode_many", "ccd_decode_coolchic", "ccd_decode_latents",
-    "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict",
+    "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict", "ccd_reconstruct_frame",
+    "ccd_pack_frame",
     "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_debug_launch_count", "ccd_debug_set_producer_mask", "ccd_debug_set_fused_synthesis", "ccd_last_timing",
 ]
 
@@ -96,7 +97,11 @@ def load_library():
         L.ccd_finish_frame.restype = ci
         L.ccd_finish_frame.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
         L.ccd_inter_predict.restype = ci
-        L.ccd_inter_predict.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp, vp]
+        L.ccd_inter_predict.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, ci, vp, ci, vp, vp]
+        L.ccd_reconstruct_frame.restype = ci
+        L.ccd_reconstruct_frame.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp, ci, vp, vp]
+        L.ccd_pack_frame.restype = ci
+        L.ccd_pack_frame.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
         L.ccd_debug_laplace_domain.restype = ci
         L.ccd_debug_laplace_domain.argtypes = [vp, ci, ci, vp, vp]
         L.ccd_debug_last_status.restype = ci
@@ -247,7 +252,7 @@ class Context:
         assert raw.is_cuda and raw.dtype == torch.float32 and raw.dim() == 4 and raw.size(1) == 3
         raw = raw.contiguous()
         h, w = raw.shape[-2:]
-        code = {"rgb": 0, "yuv420": 1, "yuv444": 2}[frame_data_type]
+        code = _frame_type_code(frame_data_type)
         if code == 1:
             y = torch.empty((1, 1, h, w), dtype=torch.float32, device=raw.device)
             u = torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=raw.device)
@@ -256,29 +261,110 @@ class Context:
                                               u.data_ptr(), v.data_ptr(), self._stream()))
             return {"y": y, "u": u, "v": v}
         out = torch.empty_like(raw)
-        _check(self._lib.ccd_finish_frame(self._h, raw.data_ptr(), h, w, bitdepth, code, out.data_ptr(), None, None,
-                                          self._stream()))
+        _check(self._lib.ccd_finish_frame(self._h, raw.data_ptr(), h, w, bitdepth, 2 if code == 3 else code,
+                                          out.data_ptr(), None, None, self._stream()))
         return out
 
-    def inter_predict(self, residue, motion, refs, is_b, frame_data_type, global_flow, warp_filter_size):
-        """decode_frame P/B branch (bitstream/decode.py:156-189) -> pre-rounding frame [1,3,H,W]."""
+    @staticmethod
+    def _check_inter_shapes(residue, motion, refs, is_b, frame_data_type):
+        """The reference fails with a shape error when the Cool-chic outputs or the references do not fit the
+        frame (decode.py:159-189); the kernels read raw pointers, so the same conditions are checked here."""
+        if residue.dim() != 4 or motion.dim() != 4 or residue.size(0) != 1 or motion.size(0) != 1:
+            raise ValueError(f"residue / motion must be [1, C, H, W], found {tuple(residue.shape)} / {tuple(motion.shape)}")
         h, w = residue.shape[-2:]
-        ref444 = []
-        for r in refs:
-            if frame_data_type == "yuv420":  # convert_420_to_444 (io/format/yuv.py:303-316): nearest x2
-                d = r.data
-                u = d["u"].repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-                v = d["v"].repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
-                ref444.append(torch.cat((d["y"], u, v), dim=1).contiguous())
-            else:
-                ref444.append(r.data.contiguous())
+        if tuple(motion.shape[-2:]) != (h, w):
+            raise ValueError(f"motion is {tuple(motion.shape[-2:])}, residue is {(h, w)}")
+        n_ref = 2 if is_b else 1
+        if residue.size(1) != 3 + n_ref:
+            raise ValueError(f"{'B' if is_b else 'P'}-frame residue needs {3 + n_ref} channels, found {residue.size(1)}")
+        if motion.size(1) != 2 * n_ref:
+            raise ValueError(f"{'B' if is_b else 'P'}-frame motion needs {2 * n_ref} channels, found {motion.size(1)}")
+        if len(refs) < n_ref:
+            raise ValueError(f"{'B' if is_b else 'P'} frame with {len(refs)} reference frame(s)")
+        for r in refs[:n_ref]:
+            if r.frame_data_type != frame_data_type:
+                raise ValueError(f"reference is {r.frame_data_type}, frame is {frame_data_type}")
+            if frame_data_type == "yuv420":
+                shapes = [tuple(r.data[k].shape) for k in ("y", "u", "v")]
+                if (h | w) & 1 or shapes != [(1, 1, h, w), (1, 1, h // 2, w // 2), (1, 1, h // 2, w // 2)]:
+                    raise ValueError(f"yuv420 reference planes {shapes} do not fit a {h}x{w} frame")
+            elif tuple(r.data.shape) != (1, 3, h, w):
+                raise ValueError(f"reference is {tuple(r.data.shape)}, frame is {(1, 3, h, w)}")
+        return h, w
+
+    @staticmethod
+    def _ref_planes(r, frame_data_type):
+        """(keep-alive tensors, c_void_p[3]) of a reference frame's planes."""
+        if frame_data_type == "yuv420":
+            ts = [r.data[k].contiguous() for k in ("y", "u", "v")]
+        else:
+            t = r.data.contiguous()
+            ts = [t[0, c] for c in range(3)]
+        assert all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+        return ts, (ctypes.c_void_p * 3)(*[t.data_ptr() for t in ts])
+
+    def inter_predict(self, residue, motion, refs, is_b, frame_data_type, global_flow, warp_filter_size):
+        """decode_frame P/B branch (bitstream/decode.py:156-189) -> PRE-ROUNDING frame [1,3,H,W] (stage entry
+        point for tests; decode_frame uses reconstruct_frame).  References are 4:4:4 here."""
+        if frame_data_type == "yuv420":
+            raise ValueError("inter_predict takes 4:4:4 references; use reconstruct_frame for yuv420 frames")
+        h, w = self._check_inter_shapes(residue, motion, refs, is_b, frame_data_type)
+        residue, motion = residue.contiguous(), motion.contiguous()
+        r0 = refs[0].data.contiguous()
+        r1 = refs[1].data.contiguous() if is_b else None
         out = torch.empty((1, 3, h, w), dtype=torch.float32, device=self.torch_device)
         gf = (ctypes.c_int32 * 4)(*(list(global_flow) + [0, 0, 0, 0])[:4])
-        residue, motion = residue.contiguous(), motion.contiguous()
         _check(self._lib.ccd_inter_predict(
-            self._h, residue.data_ptr(), motion.data_ptr(), ref444[0].data_ptr(),
-            ref444[1].data_ptr() if is_b else None, h, w, int(is_b), gf, int(warp_filter_size), out.data_ptr(),
+            self._h, residue.data_ptr(), residue.size(1), motion.data_ptr(), motion.size(1), r0.data_ptr(),
+            r1.data_ptr() if is_b else None, h, w, int(is_b), gf, int(warp_filter_size), out.data_ptr(), self._stream()))
+        return out
+
+    def reconstruct_frame(self, residue, motion, refs, is_b, frame_data_type, bitdepth, global_flow, warp_filter_size):
+        """Whole P/B reconstruction in one kernel (bitstream/decode.py:156-206): prediction from the finished
+        reference frames (4:2:0 planes read in place), blending, residue, frame tail.  Returns the finished frame
+        in FrameData layout ([1,3,H,W], or the y / u / v dictionary)."""
+        h, w = self._check_inter_shapes(residue, motion, refs, is_b, frame_data_type)
+        residue, motion = residue.contiguous(), motion.contiguous()
+        keep0, p0 = self._ref_planes(refs[0], frame_data_type)
+        keep1, p1 = self._ref_planes(refs[1], frame_data_type) if is_b else (None, None)
+        dev = self.torch_device
+        if frame_data_type == "yuv420":
+            data = {"y": torch.empty((1, 1, h, w), dtype=torch.float32, device=dev),
+                    "u": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=dev),
+                    "v": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=dev)}
+            outs = [data[k] for k in ("y", "u", "v")]
+        else:
+            data = torch.empty((1, 3, h, w), dtype=torch.float32, device=dev)
+            outs = [data[0, c] for c in range(3)]
+        po = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in outs])
+        gf = (ctypes.c_int32 * 4)(*(list(global_flow) + [0, 0, 0, 0])[:4])
+        _check(self._lib.ccd_reconstruct_frame(
+            self._h, residue.data_ptr(), residue.size(1), motion.data_ptr(), motion.size(1), p0, p1,
+            _frame_type_code(frame_data_type), int(bitdepth), h, w, int(is_b), gf, int(warp_filter_size), po,
             self._stream()))
+        del keep0, keep1
+        return data
+
+    def pack_frame(self, data, bitdepth: int, frame_data_type: str, interleaved: bool = False,
+                   sample_bytes: Optional[int] = None) -> torch.Tensor:
+        """Finished frame (FrameData.data on the device) -> integer samples on the device, uint8 / uint16:
+        planar (y, u, v one after the other: the .yuv file order) or pixel-interleaved HWC (PPM / PNG order)."""
+        if frame_data_type == "yuv420":
+            planes = [data[k].contiguous() for k in ("y", "u", "v")]
+            h, w = planes[0].shape[-2:]
+            cs = 1
+        else:
+            t = data.contiguous()
+            h, w = t.shape[-2:]
+            planes = [t[0, c] for c in range(3)]
+            cs = 0
+        if sample_bytes is None:
+            sample_bytes = 1 if bitdepth <= 8 else 2
+        n = h * w + 2 * (h >> cs) * (w >> cs)
+        out = torch.empty((n,), dtype=torch.uint8 if sample_bytes == 1 else torch.int16, device=self.torch_device)
+        pp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in planes])
+        _check(self._lib.ccd_pack_frame(self._h, pp, h, w, cs, int(bitdepth), sample_bytes, int(bool(interleaved)),
+                                        out.data_ptr(), self._stream()))
         return out
 
     def last_timing(self):
@@ -307,10 +393,21 @@ class Context:
         return lo, hi
 
 
+def _frame_type_code(frame_data_type: str) -> int:
+    """io/types.py:12 order: rgb, yuv420, yuv444, flow.  'flow' frames take the generic (4:4:4) tail like the
+    reference's decode.py:191-206 does."""
+    try:
+        return {"rgb": 0, "yuv420": 1, "yuv444": 2, "flow": 3}[frame_data_type]
+    except KeyError:
+        raise ValueError(f"unknown frame_data_type {frame_data_type!r}") from None
+
+
 _contexts = {}
+_contexts_lock = threading.Lock()
 
 
 def get_context(device: int = 0) -> Context:
-    if device not in _contexts:
-        _contexts[device] = Context(device)
-    return _contexts[device]
+    with _contexts_lock:
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]

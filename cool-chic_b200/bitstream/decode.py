@@ -52,15 +52,16 @@ def _reconstruct(frame_header: FrameHeader, cc_out: Dict[str, torch.Tensor], ref
     frame_data_type = frame_header.get_value("frame_data_type")
     if frame_type == "I":
         decoded = cc_out["residue"]
+        if decoded.size(1) != 3:
+            raise ValueError(f"Frame reconstruction expects 3 channels, found {decoded.size(1)}")
+        data = ctx.finish_frame(decoded, bitdepth, frame_data_type)
     else:
+        # prediction + blending + residue + frame tail: one kernel, 4:2:0 references read in place
         refs = [r.to(ctx.torch_device) for r in reference_frames]
-        decoded = ctx.inter_predict(
-            cc_out["residue"], cc_out["motion"], refs, frame_type == "B", frame_data_type,
+        data = ctx.reconstruct_frame(
+            cc_out["residue"], cc_out["motion"], refs, frame_type == "B", frame_data_type, bitdepth,
             frame_header.get_value("global_flow"), frame_header.get_value("warp_filter_size"),
         )
-    if decoded.size(1) != 3:
-        raise ValueError(f"Frame reconstruction expects 3 channels, found {decoded.size(1)}")
-    data = ctx.finish_frame(decoded, bitdepth, frame_data_type)
     return FrameData(bitdepth=bitdepth, frame_data_type=frame_data_type, data=data)
 
 

@@ -417,6 +417,21 @@ struct CcdContext {
 
 namespace {
 
+// Entry points run on the context's device and put the caller's current device back on return (the host
+// application -- PyTorch -- keeps its own notion of the current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 int ensure_dev(DeviceBuf &b, size_t bytes) {
     if (bytes <= b.cap) return CCD_OK;
     if (b.p) CUDA_TRY(cudaFree(b.p));
@@ -900,14 +915,39 @@ int64_t ccd_decode_nn(const CcdCoolChicDesc *desc, const uint8_t *nn_bytes, size
 }
 
 // stages: bit 0 entropy, bit 1 synthesis
+static int decode_impl_body(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t *const *nn_ints, int stages,
+                            const int8_t *const *d_lat_in, int mode, uint64_t seed, uint32_t *const *d_out_words,
+                            int64_t out_cap, int32_t (*statuses)[16], cudaStream_t st);
+
 static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t *const *nn_ints, int stages,
                        const int8_t *const *d_lat_in, int mode, uint64_t seed, uint32_t *const *d_out_words,
                        int64_t out_cap, int32_t (*statuses)[16], void *cuda_stream) {
     if (!ctx) return fail(CCD_ERR_ARG, "null context");
     if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(CCD_ERR_ARG, "bad job list");
     if (n_jobs == 0) return CCD_OK;
-    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (stages & 2)
+        for (int i = 0; i < n_jobs; i++)
+            if (!jobs[i].d_out) return fail(CCD_ERR_ARG, "job %d: null output pointer", i);
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(CCD_ERR_CUDA, "cudaSetDevice(%d) failed", ctx->device);
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int rc = decode_impl_body(ctx, jobs, n_jobs, nn_ints, stages, d_lat_in, mode, seed, d_out_words, out_cap, statuses, st);
+    if (rc != CCD_OK) {
+        // every exit path leaves the context quiescent: the pinned staging buffer, the upload arena and the scratch
+        // may be reused (or re-allocated) by the next call
+        const std::string keep = g_err;
+        cudaStreamSynchronize(st);
+        for (int a = 0; a < 3; a++)
+            if (ctx->aux[a]) cudaStreamSynchronize(ctx->aux[a]);
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+
+static int decode_impl_body(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t *const *nn_ints, int stages,
+                            const int8_t *const *d_lat_in, int mode, uint64_t seed, uint32_t *const *d_out_words,
+                            int64_t out_cap, int32_t (*statuses)[16], cudaStream_t st) {
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
     std::vector<PreparedJob> P((size_t)n_jobs);
@@ -1024,12 +1064,10 @@ static int decode_impl(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int64_t 
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (stages & 2) {
         for (int i = 0; i < n_jobs; i++) {
-            if (!jobs[i].d_out) return fail(CCD_ERR_ARG, "job %d: null output pointer", i);
             rc = run_synthesis(ctx, P[(size_t)i], d_lat[(size_t)i], reinterpret_cast<const float *>(dv + P[(size_t)i].off_syn),
                                jobs[i].d_out, d_scr_syn, scratch_syn, st);
             if (rc) {
                 jobs[i].status = rc;
-                cudaStreamSynchronize(st);
                 return rc;
             }
         }
@@ -1105,30 +1143,96 @@ int ccd_finish_frame(CcdContext *ctx, const float *d_in, int h, int w, int bitde
     if (!ctx || !d_in || !d_out_a || h < 1 || w < 1 || bitdepth < 8 || bitdepth > 16 || data_type < 0 || data_type > 2)
         return fail(CCD_ERR_ARG, "bad argument");
     if (data_type == 1 && (!d_out_b || !d_out_c)) return fail(CCD_ERR_ARG, "yuv420 needs u and v outputs");
-    CUDA_TRY(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(CCD_ERR_CUDA, "cudaSetDevice failed");
     if (ccd_finish(d_in, h, w, bitdepth, data_type, d_out_a, d_out_b, d_out_c, (cudaStream_t)cuda_stream))
         return fail(CCD_ERR_CUDA, "finish_frame launch failed");
     return CCD_OK;
 }
 
-int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_motion, const float *d_ref0,
-                      const float *d_ref1, int h, int w, int is_b, const int32_t *global_flow, int warp_filter_size,
-                      float *d_out, void *cuda_stream) {
-    if (!ctx || !d_residue || !d_motion || !d_ref0 || !d_out || !global_flow || h < 2 || w < 2 || (is_b && !d_ref1))
+namespace {
+int inter_common(CcdContext *ctx, InterLaunch &L, int n_res_ch, int n_mot_ch, void *cuda_stream) {
+    if (!ctx || !L.residue || !L.motion || !L.ref0[0] || !L.ref0[1] || !L.ref0[2] || !L.out[0] || !L.out[1] || !L.out[2] ||
+        L.h < 1 || L.w < 1)
         return fail(CCD_ERR_ARG, "bad argument");
-    if (warp_filter_size < 2 || (warp_filter_size & 1)) return fail(CCD_ERR_ARG, "bad warp filter size %d", warp_filter_size);
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    int32_t gf[4] = {global_flow[0], global_flow[1], is_b ? global_flow[2] : 0, is_b ? global_flow[3] : 0};
-    int rc = ccd_inter_launch(d_residue, d_motion, d_ref0, d_ref1, h, w, is_b, gf, warp_filter_size, d_out,
-                              (cudaStream_t)cuda_stream);
-    if (rc == -1) return fail(CCD_ERR_UNSUPPORTED, "warp filter size %d is not instantiated (2, 4, 6, 8, 10, 12 are; 2 and 4 need a frame of at least 2x2)", warp_filter_size);
+    if (L.is_b && (!L.ref1[0] || !L.ref1[1] || !L.ref1[2])) return fail(CCD_ERR_ARG, "B frame without a second reference");
+    // decode.py:171-189 reads residue channels 0..3 (P) / 0..4 (B) and motion channels 0..1 (P) / 0..3 (B)
+    if (n_res_ch != (L.is_b ? 5 : 4))
+        return fail(CCD_ERR_ARG, "%s-frame residue has %d channels, expected %d", L.is_b ? "B" : "P", n_res_ch, L.is_b ? 5 : 4);
+    if (n_mot_ch != (L.is_b ? 4 : 2))
+        return fail(CCD_ERR_ARG, "%s-frame motion has %d channels, expected %d", L.is_b ? "B" : "P", n_mot_ch, L.is_b ? 4 : 2);
+    if ((L.ref_cs || L.out_420) && ((L.h | L.w) & 1)) return fail(CCD_ERR_ARG, "4:2:0 needs even frame sizes, got %dx%d", L.h, L.w);
+    if (L.filter_size < 2 || (L.filter_size & 1)) return fail(CCD_ERR_ARG, "bad warp filter size %d", L.filter_size);
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(CCD_ERR_CUDA, "cudaSetDevice failed");
+    if (!L.is_b) L.gf[2] = L.gf[3] = 0;
+    int rc = ccd_inter_launch(L, (cudaStream_t)cuda_stream);
+    if (rc == -1)
+        return fail(CCD_ERR_UNSUPPORTED, "warp filter size %d is not supported (2, 4: frames of at least 2x2; 6 .. 14)", L.filter_size);
     if (rc) return fail(CCD_ERR_CUDA, "inter_predict launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    return CCD_OK;
+}
+}  // namespace
+
+int ccd_inter_predict(CcdContext *ctx, const float *d_residue, int n_res_ch, const float *d_motion, int n_mot_ch,
+                      const float *d_ref0, const float *d_ref1, int h, int w, int is_b, const int32_t *global_flow,
+                      int warp_filter_size, float *d_out, void *cuda_stream) {
+    if (!global_flow || !d_ref0 || !d_out) return fail(CCD_ERR_ARG, "bad argument");
+    const size_t plane = (size_t)h * w;
+    InterLaunch L{};
+    L.residue = d_residue;
+    L.motion = d_motion;
+    for (int c = 0; c < 3; c++) {
+        L.ref0[c] = d_ref0 + c * plane;
+        L.ref1[c] = d_ref1 ? d_ref1 + c * plane : nullptr;
+        L.out[c] = d_out + c * plane;
+    }
+    L.h = h; L.w = w; L.is_b = is_b;
+    for (int i = 0; i < 4; i++) L.gf[i] = (i < 2 || is_b) ? global_flow[i] : 0;
+    L.filter_size = warp_filter_size;
+    return inter_common(ctx, L, n_res_ch, n_mot_ch, cuda_stream);
+}
+
+int ccd_reconstruct_frame(CcdContext *ctx, const float *d_residue, int n_res_ch, const float *d_motion, int n_mot_ch,
+                          const float *const ref0_planes[3], const float *const ref1_planes[3], int frame_data_type,
+                          int bitdepth, int h, int w, int is_b, const int32_t *global_flow, int warp_filter_size,
+                          float *const out_planes[3], void *cuda_stream) {
+    if (!global_flow || !ref0_planes || !out_planes) return fail(CCD_ERR_ARG, "bad argument");
+    if (bitdepth < 1 || bitdepth > 16) return fail(CCD_ERR_ARG, "bad bitdepth %d", bitdepth);
+    if (frame_data_type < 0 || frame_data_type > 3) return fail(CCD_ERR_ARG, "bad frame_data_type %d", frame_data_type);
+    InterLaunch L{};
+    L.residue = d_residue;
+    L.motion = d_motion;
+    for (int c = 0; c < 3; c++) {
+        L.ref0[c] = ref0_planes[c];
+        L.ref1[c] = (is_b && ref1_planes) ? ref1_planes[c] : nullptr;
+        L.out[c] = out_planes[c];
+    }
+    L.ref_cs = L.out_420 = (frame_data_type == 1);
+    L.h = h; L.w = w; L.is_b = is_b;
+    for (int i = 0; i < 4; i++) L.gf[i] = (i < 2 || is_b) ? global_flow[i] : 0;
+    L.filter_size = warp_filter_size;
+    L.M = (float)((1 << bitdepth) - 1);
+    return inter_common(ctx, L, n_res_ch, n_mot_ch, cuda_stream);
+}
+
+int ccd_pack_frame(CcdContext *ctx, const float *const planes[3], int h, int w, int chroma_shift, int bitdepth,
+                   int sample_bytes, int interleaved, void *d_out, void *cuda_stream) {
+    if (!ctx || !planes || !planes[0] || !planes[1] || !planes[2] || !d_out || h < 1 || w < 1) return fail(CCD_ERR_ARG, "bad argument");
+    if (bitdepth < 1 || bitdepth > 16 || (sample_bytes != 1 && sample_bytes != 2) || (sample_bytes == 1 && bitdepth > 8))
+        return fail(CCD_ERR_ARG, "bitdepth %d does not fit %d-byte samples", bitdepth, sample_bytes);
+    if (chroma_shift < 0 || chroma_shift > 1 || (interleaved && chroma_shift)) return fail(CCD_ERR_ARG, "bad layout");
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(CCD_ERR_CUDA, "cudaSetDevice failed");
+    if (ccd_pack(planes, h, w, chroma_shift, bitdepth, sample_bytes, interleaved, d_out, (cudaStream_t)cuda_stream))
+        return fail(CCD_ERR_CUDA, "pack_frame launch failed");
     return CCD_OK;
 }
 
 int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *out_lo, uint32_t *out_hi) {
     if (!ctx || sc_lo < 0 || sc_hi > CCD_N_SCALE || sc_lo >= sc_hi || !out_lo || !out_hi) return fail(CCD_ERR_ARG, "bad argument");
-    CUDA_TRY(cudaSetDevice(ctx->device));
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(CCD_ERR_CUDA, "cudaSetDevice failed");
     const size_t n = (size_t)(sc_hi - sc_lo) * 32641;
     int rc;
     if ((rc = ensure_dev(ctx->scratch, n * 8))) return rc;

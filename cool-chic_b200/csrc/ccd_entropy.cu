@@ -504,17 +504,19 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
             const uint4 fb = make_uint4(fix_left(vb.x, s0 + 4), fix_left(vb.y, s0 + 5), fix_left(vb.z, s0 + 6),
                                         fix_left(vb.w, s0 + 7));
             sts_v4(wdst + 32u * member + 16u, fb);
-            // hot entry (the coder's steady state reads nothing else): window entries 13 .. 16
+            // hot entry (the coder's steady state reads nothing else): window entries 13 .. 16 =
+            // left(M-1), left(M), left(M+1), left(M+2); the ring's first entries are mirrored behind its end so that
+            // a group of consecutive entries is read from one base address
             static_assert(CCD_WIN_HALF == 14, "hot entry layout");
             const uint32_t hdst = sm.hot + slot * 16u;
             const bool mirror = slot < CCD_HOT_MIRROR;
             const uint32_t hmir = hdst + (uint32_t)S.ring * 16u;
             if (member == 1) {
-                sts_v2(hdst, make_uint2(fb.z, fb.w - fb.z));
-                sts_u32(hdst + 8u, fb.y);
+                sts_v2(hdst, make_uint2(fb.y, fb.z));
+                sts_u32(hdst + 8u, fb.w);
                 if (mirror) {
-                    sts_v2(hmir, make_uint2(fb.z, fb.w - fb.z));
-                    sts_u32(hmir + 8u, fb.y);
+                    sts_v2(hmir, make_uint2(fb.y, fb.z));
+                    sts_u32(hmir + 8u, fb.w);
                 }
             } else if (member == 2) {
                 const uint32_t l16 = fix_left(va.x, s0);
@@ -536,8 +538,8 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
             {
                 const uint32_t l13 = fix_left(v[3].y, s_lo + 13), l14 = fix_left(v[3].z, s_lo + 14);
                 const uint32_t l15 = fix_left(v[3].w, s_lo + 15), l16 = fix_left(v[4].x, s_lo + 16);
-                sts_v4(sm.hot + slot * 16u, make_uint4(l14, l15 - l14, l13, l16));
-                if (slot < CCD_HOT_MIRROR) sts_v4(sm.hot + (slot + (uint32_t)S.ring) * 16u, make_uint4(l14, l15 - l14, l13, l16));
+                sts_v4(sm.hot + slot * 16u, make_uint4(l13, l14, l15, l16));
+                if (slot < CCD_HOT_MIRROR) sts_v4(sm.hot + (slot + (uint32_t)S.ring) * 16u, make_uint4(l13, l14, l15, l16));
             }
             __threadfence_block();
         }
@@ -550,6 +552,9 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
                                                 (uint32_t)mu_idx | ((uint32_t)sc_idx << 16), ord + 1u));
     }
     PROF_ADD(pc.win, t2);
+#ifdef CCD_PROFILE
+    pc.seg[5]++;
+#endif
 }
 
 template <int NCTX, int CF, bool FAST>
@@ -670,53 +675,91 @@ __device__ __noinline__ void encoder_emit(const SLoc &S, Coder &c, uint32_t L0, 
 // =======================================================================================
 struct DecState {
     uint64_t D, R;        // D = point - lower (mod 2^64), R = range   
-    int64_t wpos;         // index of the next unread word
-    uint32_t wcur, wnxt;  // lane l holds word (32*chunk + l) of the current / next chunk
-    uint32_t wnext;       // word[wpos], broadcast
-    uint32_t slow;
-    uint32_t n_far;       // symbols that were not the mode (instrumented build)
+    uint32_t w0;          // word[wpos]: the next unread word of the stream
+    uint32_t wpos;        // index of the next unread word
+    uint32_t wcur, wnxt;  // lane l holds words wbase + l and wbase + 32 + l
+    uint32_t wbase;
+    uint32_t slow;        // symbols decoded with the exact f64 model (outside the 31-symbol window)
+    uint32_t n_far;       // symbols outside {M-1, M, M+1} (instrumented build)
+    uint32_t n_redo;      // fast groups decoded again one symbol at a time (instrumented build)
     int err;
 };
 
-__device__ __noinline__ void dec_advance_word(const SLoc &S, DecState &c, int lane) {
-    c.wpos++;
-    if ((c.wpos & 31) == 0) {
-        c.wcur = c.wnxt;
-        c.wnxt = load_word(S, c.wpos + 32 + lane);
-    }
-    c.wnext = __shfl_sync(0xffffffffu, c.wcur, (int)(c.wpos & 31));
+// word i of the stream; the host pads the payload with zero words (missing words read as 0 like
+// constriction does), the index is clamped so that a corrupt stream cannot run away
+__device__ __forceinline__ uint32_t coder_word(const uint32_t *__restrict__ words, uint32_t wmax, uint32_t i) {
+    return __ldg(words + (i < wmax ? i : wmax));
 }
 
-// result word of a symbol j that is not the mode: [31] value is the symbol itself (else the window index t),
-// [30] valid (an all-zero word never matches), [29:8] tag = (j + 1) mod 2^22, [7:0] value
+// The compressed words reach the coder through REGISTERS: lane l of the coder warp keeps words wbase + l and
+// wbase + 32 + l; word[wpos] is one shuffle away (requested right after a symbol, consumed by the next one: no
+// memory instruction, hence no scoreboard wait, on the serial chain).  wbase advances at group boundaries.
+__device__ __forceinline__ uint32_t word_at(uint32_t wcur, uint32_t wnxt, uint32_t wbase, uint32_t i) {
+    const uint32_t idx = i - wbase;  // 0 .. 63
+    return __shfl_sync(0xffffffffu, (idx & 32u) ? wnxt : wcur, (int)idx);
+}
+
+// Result word of a symbol j that is NOT the mode (coder -> helper): [31] the value is the symbol itself (else the
+// window index t), [30] valid (an all-zero word never matches), [29:8] tag = (j + 1) mod 2^22, [7:0] value.
+// Mode symbols leave no trace: the helper infers them from `done` and the absence of a tagged word.
 __device__ __forceinline__ uint32_t res_tag(uint32_t j) { return 0x40000000u | (((j + 1u) & 0x3fffffu) << 8); }
-__device__ __forceinline__ uint32_t res_word(uint32_t j, uint32_t value, bool is_symbol) {
-    return ((uint32_t)is_symbol << 31) | res_tag(j) | (value & 0xffu);
+
+// ---------------------------------------------------------------------------------------------------------------
+// The recursion, two tiers (cycle figures: tools/ubench/steps.cu on a B200, one warp):
+//
+// TIER 1 -- "is it the mode?", branch-free, K symbols per branch.  h = (left(M-1), left(M), left(M+1), left(M+2))
+//   of the most probable symbol M.  With scale = R >> 24, lo = scale * left(M), rn = scale * p(M), Dn = D - lo:
+//   hi32(Dn) < hi32(rn) implies both Dn < rn (the symbol is M) and rn >= 2^32 (no renormalisation); then D = Dn,
+//   R = rn and NOTHING is written.  The loop-carried chain is shift -> multiply -> R (~30 cycles / symbol for a group
+//   of four, against ~86 for a step that decides three candidates with selects and ~52 for one branch per symbol).
+//   The K flags are tested together; when one fails the state BEFORE the first failing symbol is taken from the
+//   registers of the group (selects) and that symbol goes through tier 2.
+// TIER 2 -- one symbol, any case: M-1 / M / M+1 decided with selects (a branch on fresh data costs this warp ~30
+//   cycles, a select ~5), renormalisation with selects, the word from a register; anything else (`far`: ~1 % of the
+//   symbols of a natural image) searches the 32-entry window lane-parallel, then the exact f64 model.
+// ---------------------------------------------------------------------------------------------------------------
+struct FastOut {
+    uint32_t t;    // window index of the decoded symbol (CCD_WIN_HALF - 1 .. CCD_WIN_HALF + 1)
+    uint32_t far;  // != 0: not one of the three candidates (everything this step produced is to be discarded)
+};
+__device__ __forceinline__ FastOut fast_step(uint64_t &D, uint64_t &R, uint32_t &w0, uint32_t &wpos, const uint32_t wcur,
+                                             const uint32_t wnxt, const uint32_t wbase, const uint4 h) {
+    const uint64_t scale = R >> 24;
+    const uint64_t P0 = scale * h.x, P1 = scale * h.y, P2 = scale * h.z, P3 = scale * h.w;
+    const bool c1 = D >= P1, c2 = D >= P2;
+    FastOut o;
+    o.far = (uint32_t)(D < P0) | (uint32_t)(D >= P3);
+    const uint64_t nlo = c2 ? P2 : (c1 ? P1 : P0);
+    const uint64_t nhi = c2 ? P3 : (c1 ? P2 : P1);
+    const uint64_t Dn = D - nlo, Rn = nhi - nlo;
+    const bool renorm = (uint32_t)(Rn >> 32) == 0u;
+    D = renorm ? ((Dn << 32) | w0) : Dn;
+    R = renorm ? (Rn << 32) : Rn;
+    wpos += renorm ? 1u : 0u;
+    w0 = word_at(wcur, wnxt, wbase, wpos);
+    o.t = c2 ? (CCD_WIN_HALF + 1u) : (c1 ? (uint32_t)CCD_WIN_HALF : (CCD_WIN_HALF - 1u));
+    return o;
 }
 
-// Out-of-line parts of the coder take and return everything BY VALUE (registers), never through a
-// reference into the kernel's local-memory state.
+// Exact path of one symbol that is not M-1 / M / M+1: the whole 32-entry window at once (lane per entry:
+// one conflict-free LDS, one product, one vote -- the cost does not depend on how far from the mode the
+// symbol is), then the exact f64 model (warp-cooperative) outside the window.  Out of line, by value.
 struct FarOut {
-    uint64_t lo, hi;
-    uint32_t rw;
-    uint32_t flags;  // 2: outside the window (exact search), 4: desynchronised
+    uint64_t lo, hi;  // scale * left(sym), scale * left(sym + 1)
+    uint32_t rw;      // result word (without the tag)
+    uint32_t flags;   // 2: outside the window (exact search), 4: desynchronised
 };
-
-// Symbol is neither the mode nor one of its two neighbours: the whole 32-entry window at once (lane per
-// entry), then the exact f64 model (warp-cooperative).
 __device__ __noinline__ FarOut coder_far(uint32_t wrow, uint32_t meta_slot, const float *__restrict__ scale_tab, int lane,
-                                         uint32_t j, uint64_t scale, uint64_t D) {
+                                         uint64_t scale, uint64_t D) {
     FarOut o;
     o.flags = 0;
-    // lane t evaluates window entry t: one conflict-free LDS, one product, one vote -- the cost does not
-    // depend on how far from the mode the symbol is (wide distributions of the coarse grids)
     const uint32_t Lt = lds_u32(wrow + 4u * (uint32_t)lane);
     const uint32_t b = __ballot_sync(0xffffffffu, scale * Lt <= D);  // lefts are non-decreasing: bits 0..t
     if (b != 0u && b != 0xffffffffu) {
         const int t = 31 - __clz((int)b);
         o.lo = scale * (uint64_t)__shfl_sync(0xffffffffu, Lt, t);
         o.hi = scale * (uint64_t)__shfl_sync(0xffffffffu, Lt, t + 1);
-        o.rw = res_word(j, (uint32_t)t, false);
+        o.rw = (uint32_t)t;
         return o;
     }
     // outside the window, or corrupt stream
@@ -730,180 +773,69 @@ __device__ __noinline__ FarOut coder_far(uint32_t wrow, uint32_t meta_slot, cons
     const uint4 r = slow_search((uint32_t)q, (int)(m.z & 0xffffu), (int)(m.z >> 16), scale_tab, lane);
     o.lo = scale * (uint64_t)__shfl_sync(0xffffffffu, r.x, (int)r.z);
     o.hi = scale * (uint64_t)__shfl_sync(0xffffffffu, r.y, (int)r.z);
-    o.rw = res_word(j, r.w, true);
+    o.rw = 0x80000000u | (r.w & 0xffu);
     return o;
 }
 
-// Everything that is not "the mode, no renormalisation": the two neighbours of the mode from the hot
-// entry, any other symbol through coder_far, the result word for the helper, the renormalisation.
-// Out of line (about one symbol in seven): the steady loop stays ~20 instructions per symbol.
-struct SlowOut {
-    uint32_t d_lo, d_hi, r_lo, r_hi;  // (D, R) after the symbol
-    uint32_t flags;                   // 1: consumed the next word, 2 / 4: see FarOut, 8: not the mode
-};
-__device__ __noinline__ SlowOut coder_slow(uint32_t res_a, uint32_t win_a, uint32_t meta_a,
-                                           const float *__restrict__ scale_tab, uint32_t ring_mask, int lane, uint32_t j,
-                                           uint4 h, uint64_t D, uint64_t R, uint32_t wnext) {
-    // Branches are what costs on this warp (~30 cycles each: predicate wait + fetch redirect, measured), so
-    // the mode and its two neighbours are decided with selects; only "none of the three" and the
-    // renormalisation bookkeeping branch (both rare).
-    constexpr uint32_t M = CCD_WIN_HALF;
-    const uint64_t scale = R >> 24;
-    const uint64_t lo = scale * h.x, rn = scale * h.y;
-    const uint64_t hiM = lo + rn;  // = scale * left(M + 1)
-    // which neighbour can it be?  D < lo: only the left one (needs left(M-1)), else only the right one (left(M+2))
-    const bool is_m = (D - lo) < rn;
-    const bool below = D < lo;
-    const uint64_t pn = scale * (below ? h.z : h.w);
-    const bool is_l = below & (pn <= D);
-    const bool is_r = (!below) & (hiM <= D) & (D < pn);
-    uint64_t nlo = is_m ? lo : (is_l ? pn : hiM);
-    uint64_t nhi = is_m ? hiM : (is_l ? lo : pn);
-    uint32_t rw = res_tag(j) | (is_l ? (M - 1u) : (M + 1u));
-    const uint32_t slot = j & ring_mask;
-    uint32_t flags = is_m ? 0u : 8u;
-    if (!(is_m | is_l | is_r)) {
-        const FarOut f = coder_far(win_a + slot * (CCD_WIN * 4), meta_a + slot * 16u, scale_tab, lane, j, scale, D);
-        nlo = f.lo;
-        nhi = f.hi;
-        rw = f.rw;
-        flags |= f.flags;
-    }
-    uint64_t Dn = D - nlo, Rn = nhi - nlo;
-    // shared-memory stores of one warp are performed in program order: this word is visible before the
-    // `done` store that follows it
-    if (!is_m && lane == 0) sts_u32(res_a + slot * 4u, rw);
-    const bool renorm = (Rn >> 32) == 0;  // at most one renormalisation per symbol
-    Dn = renorm ? ((Dn << 32) | wnext) : Dn;
-    Rn = renorm ? (Rn << 32) : Rn;
-    flags |= renorm ? 1u : 0u;
-    SlowOut o;
-    o.d_lo = (uint32_t)Dn;
-    o.d_hi = (uint32_t)(Dn >> 32);
-    o.r_lo = (uint32_t)Rn;
-    o.r_hi = (uint32_t)(Rn >> 32);
-    o.flags = flags;
-    return o;
-}
-
-// The rare follow-ups of coder_slow that touch the (local-memory) decoder state.
-__device__ __noinline__ uint32_t coder_bookkeeping(const SLoc &S, DecState &c, int lane, uint32_t flags) {
-    if (flags & 1u) dec_advance_word(S, c, lane);
-    if (flags & 2u) c.slow++;
-    if (flags & 4u) c.err = CCD_ERR_DESYNC;
-    return c.wnext;
-}
-
-// One symbol of the recursion, executed IDENTICALLY by every lane of the coder warp: no vote, no
-// shuffle, no shared-memory round trip on the serial chain -- two 64-bit products, one subtraction and
-// one unsigned compare.  h = (left(M), left(M+1) - left(M), ..) of the most probable symbol M:
-// D - scale*left(M) < scale*p(M) (wrapping) <=> the symbol is M;  new R = scale*p(M).
-// Nothing is written for a mode symbol: the helper learns it from `done` and the absence of a result word.
-#ifdef CCD_PROFILE
-#define CODER_COUNT_FAR(F) c.n_far += ((F) >> 3) & 1u
-#define CODER_SLOW_T0 const long long ts_ = clock64()
-#define CODER_SLOW_T1 pc.seg[2] += clock64() - ts_; pc.seg[0]++
-#else
-#define CODER_COUNT_FAR(F)
-#define CODER_SLOW_T0
-#define CODER_SLOW_T1
+#ifndef CCD_FAST_K
+#define CCD_FAST_K 4  // symbols per tier-1 group
 #endif
-// The test: with Dn = D - scale*left(M) (wrapping) and Rn = scale*p(M), "symbol is M and no
-// renormalisation" <=> Dn < Rn and Rn >= 2^32.  hi32(Dn) < hi32(Rn) implies both; the converse fails only
-// when the two high words are equal (probability ~ 1 / hi32(Rn)): those go to coder_slow too, which decides
-// exactly.  One 32-bit compare per symbol instead of a 64-bit compare chain plus a range test.
-//
-// Software pipelining: the branch of symbol j has to wait for that compare, so the products of symbol
-// j+1 are issued BEFORE it, from Rn (the state if j is the mode, the common case), and redone after
-// coder_slow otherwise.  The loop-carried chain is R -> shift -> multiply -> R.
-#define CODER_SLOW(JJ, H)                                                                                   \
-    do {                                                                                                    \
-        CODER_SLOW_T0;                                                                                      \
-        const SlowOut r_ = coder_slow(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, (JJ), (H), D, R, wnext); \
-        D = ((uint64_t)r_.d_hi << 32) | r_.d_lo;                                                            \
-        R = ((uint64_t)r_.r_hi << 32) | r_.r_lo;                                                            \
-        CODER_COUNT_FAR(r_.flags);                                                                          \
-        if (r_.flags & 7u) wnext = coder_bookkeeping(S, c, lane, r_.flags);                                 \
-        CODER_SLOW_T1;                                                                                      \
-    } while (0)
-// products of a symbol from the current R
-#define CODER_PRE(H)                                                                                        \
-    do {                                                                                                    \
-        const uint64_t scale_ = R >> 24;                                                                    \
-        lo = scale_ * (H).x;                                                                                \
-        rn = scale_ * (H).y;                                                                                \
-    } while (0)
-// symbol JJ (products in lo, rn), then the products of the next symbol (hot entry HN).  Written in PTX
-// and volatile so that the look-ahead products stay ABOVE the branch (the compiler otherwise proves
-// them equal to CODER_PRE after the join and sinks them below it, back onto the serial chain).
-__device__ __forceinline__ uint32_t coder_spec(uint64_t D, uint64_t lo, uint64_t rn, uint32_t nL, uint32_t nP, uint64_t &dn,
-                                           uint64_t &lo2, uint64_t &rn2) {
-    uint32_t dn_lo, dn_hi, l2_lo, l2_hi, r2_lo, r2_hi, ok;
-    asm volatile(
-        "{\n"
-        " .reg .u32 s_lo, s_hi, t;\n"
-        " .reg .pred p;\n"
-        " sub.cc.u32 %0, %7, %9;\n"
-        " subc.u32 %1, %8, %10;\n"
-        " shf.r.clamp.b32 s_lo, %11, %12, 24;\n"
-        " shr.u32 s_hi, %12, 24;\n"
-        " mul.lo.u32 %2, s_lo, %13;\n"
-        " mul.hi.u32 t, s_lo, %13;\n"
-        " mad.lo.u32 %3, s_hi, %13, t;\n"
-        " mul.lo.u32 %4, s_lo, %14;\n"
-        " mul.hi.u32 t, s_lo, %14;\n"
-        " mad.lo.u32 %5, s_hi, %14, t;\n"
-        " setp.lt.u32 p, %1, %12;\n"
-        " selp.u32 %6, 1, 0, p;\n"
-        "}\n"
-        : "=r"(dn_lo), "=r"(dn_hi), "=r"(l2_lo), "=r"(l2_hi), "=r"(r2_lo), "=r"(r2_hi), "=r"(ok)
-        : "r"((uint32_t)D), "r"((uint32_t)(D >> 32)), "r"((uint32_t)lo), "r"((uint32_t)(lo >> 32)), "r"((uint32_t)rn),
-          "r"((uint32_t)(rn >> 32)), "r"(nL), "r"(nP));
-    dn = ((uint64_t)dn_hi << 32) | dn_lo;
-    lo2 = ((uint64_t)l2_hi << 32) | l2_lo;
-    rn2 = ((uint64_t)r2_hi << 32) | r2_lo;
-    return ok;
-}
-#define CODER_STEP_SPEC(JJ, H, HN)                                                                          \
-    do {                                                                                                    \
-        uint64_t dn_, lo2_, rn2_;                                                                           \
-        if (__builtin_expect(coder_spec(D, lo, rn, (HN).x, (HN).y, dn_, lo2_, rn2_) != 0u, 1)) {                                       \
-            D = dn_;                                                                                        \
-            R = rn;                                                                                         \
-            lo = lo2_;                                                                                      \
-            rn = rn2_;                                                                                      \
-        } else {                                                                                            \
-            CODER_SLOW(JJ, H);                                                                              \
-            CODER_PRE(HN);                                                                                  \
-        }                                                                                                   \
-    } while (0)
-// symbol JJ (products in lo, rn) without look-ahead
-#define CODER_STEP_LAST(JJ, H)                                                                              \
-    do {                                                                                                    \
-        const uint64_t dn_ = D - lo;                                                                        \
-        if ((uint32_t)(dn_ >> 32) < (uint32_t)(rn >> 32)) {                                                 \
-            D = dn_;                                                                                        \
-            R = rn;                                                                                         \
-        } else {                                                                                            \
-            CODER_SLOW(JJ, H);                                                                              \
-        }                                                                                                   \
-    } while (0)
 
 __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
                                            int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
                                            ProfCounters &pc) {
+    constexpr int K = CCD_FAST_K;
+    static_assert(K >= 2 && K <= CCD_HOT_MIRROR, "group size");
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
     const uint32_t ready_a = sm.ctrl + 4u, done_a = sm.ctrl + 8u;
+    const uint32_t *__restrict__ words = S.words;
+    const uint32_t wmax = (uint32_t)S.n_words + 1u;  // words[n_words .. n_words + 3] are zero (host padding)
     uint64_t D = c.D, R = c.R;
-    uint64_t lo = 0, rn = 0;
-    uint32_t wnext = c.wnext;
+    uint32_t w0 = c.w0, wpos = c.wpos, wcur = c.wcur, wnxt = c.wnxt, wbase = c.wbase;
     uint32_t j = ord_begin;
     uint32_t limit = ord_begin;  // symbols < limit have their window in the ring
     auto refresh = [&]() {
         const uint32_t r = lds_u32(ready_a);
         limit = ((int32_t)(r - ord_end) > 0) ? ord_end : r;
     };
-    auto hot_of = [&](uint32_t jj) { return lds_v4(sm.hot + (jj & ring_mask) * 16u); };
+    // TIER 2: symbol j, its hot entry in hh; publishes `done`
+    auto single = [&](const uint4 hh) {
+        if (wpos - wbase >= 32u) {  // the lane-held words move on
+            wcur = wnxt;
+            wbase += 32u;
+            wnxt = coder_word(words, wmax, wbase + 32u + (uint32_t)lane);
+        }
+        const uint64_t D0 = D, R0 = R;
+        const uint32_t w00 = w0, wp0 = wpos;
+        const FastOut f = fast_step(D, R, w0, wpos, wcur, wnxt, wbase, hh);
+        uint32_t rw = f.t;
+        if (f.far) {
+            const uint32_t slot = j & ring_mask;
+            const uint64_t scale = R0 >> 24;
+            const FarOut o = coder_far(sm.win + slot * (CCD_WIN * 4), sm.meta + slot * 16u, scale_tab, lane, scale, D0);
+            uint64_t Dn = D0 - o.lo, Rn = o.hi - o.lo;
+            w0 = w00;
+            wpos = wp0;
+            if ((Rn >> 32) == 0) {
+                Dn = (Dn << 32) | w0;
+                Rn <<= 32;
+                wpos++;
+                w0 = word_at(wcur, wnxt, wbase, wpos);
+            }
+            D = Dn;
+            R = Rn;
+            rw = o.rw;
+            if (o.flags & 2u) c.slow++;
+            if (o.flags & 4u) c.err = CCD_ERR_DESYNC;
+#ifdef CCD_PROFILE
+            c.n_far++;
+#endif
+        }
+        // shared-memory stores of one warp are performed in program order: the word is visible before `done`
+        if (rw != (uint32_t)CCD_WIN_HALF) sts_u32(sm.res + (j & ring_mask) * 4u, res_tag(j) | rw);
+        j++;
+        sts_u32(done_a, j);
+    };
     while (j != ord_end) {
         if ((int32_t)(limit - j) <= 0) {
             PROF_T(t0);
@@ -912,55 +844,85 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             } while ((int32_t)(limit - j) <= 0);
             PROF_ADD(pc.wait, t0);
         }
-        if ((int32_t)(limit - j) >= 3) {
-            // at least a triple is ready.  Steady state (9 or more ready): six symbols per round trip through
-            // the loop: the hot entries of the next triple
-            // are requested while a triple is decoded, and the two register sets swap roles (no copies);
-            // the ring's first entries are mirrored behind its end, so one address serves a triple
-            uint32_t o = sm.hot + (j & ring_mask) * 16u;
-            uint4 a0 = lds_v4(o), a1 = lds_v4(o + 16u), a2 = lds_v4(o + 32u);
-            CODER_PRE(a0);
-            while ((int32_t)(limit - j) >= 9) {
-                o = sm.hot + ((j + 3u) & ring_mask) * 16u;
-                const uint4 b0 = lds_v4(o), b1 = lds_v4(o + 16u), b2 = lds_v4(o + 32u);
-                CODER_STEP_SPEC(j, a0, a1);
-                CODER_STEP_SPEC(j + 1u, a1, a2);
-                CODER_STEP_SPEC(j + 2u, a2, b0);
-                sts_u32(done_a, j + 3u);  // every lane stores the same word: no predicate on the hot path
-                o = sm.hot + ((j + 6u) & ring_mask) * 16u;
-                a0 = lds_v4(o);
-                a1 = lds_v4(o + 16u);
-                a2 = lds_v4(o + 32u);
-                CODER_STEP_SPEC(j + 3u, b0, b1);
-                CODER_STEP_SPEC(j + 4u, b1, b2);
-                CODER_STEP_SPEC(j + 5u, b2, a0);
-                j += 6u;
-                sts_u32(done_a, j);
-#ifdef CCD_PROFILE
-                pc.seg[3] += 6;
-#endif
-                if ((int32_t)(limit - j) < 9) refresh();
-            }
-            // a0..a2 are valid (limit - j >= 3 here), lo / rn belong to a0
-            CODER_STEP_SPEC(j, a0, a1);
-            CODER_STEP_SPEC(j + 1u, a1, a2);
-            CODER_STEP_LAST(j + 2u, a2);
-            j += 3u;
-            sts_u32(done_a, j);
-        } else {
-            const uint4 a0 = hot_of(j);
-            CODER_PRE(a0);
-            CODER_STEP_LAST(j, a0);
-            j++;
-            sts_u32(done_a, j);
+        if ((int32_t)(limit - j) < 2 * K) {
+            // the coder is close behind the producers (small grids, where the ARM latency bounds the stream)
+            single(lds_v4(sm.hot + (j & ring_mask) * 16u));
 #ifdef CCD_PROFILE
             pc.seg[4]++;
 #endif
+            continue;
+        }
+        // ---- steady state: tier-1 groups
+        uint32_t o = sm.hot + (j & ring_mask) * 16u;  // (the ring's first entries are mirrored behind its end)
+        uint4 a[K], b[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) a[i] = lds_v4(o + 16u * i);
+        while (true) {
+            if ((int32_t)(limit - j) < 2 * K) {
+                refresh();
+                if ((int32_t)(limit - j) < 2 * K) break;
+            }
+            o = sm.hot + ((j + K) & ring_mask) * 16u;
+#pragma unroll
+            for (int i = 0; i < K; i++) b[i] = lds_v4(o + 16u * i);
+            uint64_t Ds[K + 1], Rs[K + 1];
+            uint32_t bad[K];
+            Ds[0] = D;
+            Rs[0] = R;
+#pragma unroll
+            for (int i = 0; i < K; i++) {
+                const uint64_t scale = Rs[i] >> 24;
+                const uint64_t lo = scale * a[i].y, rn = scale * (a[i].z - a[i].y);
+                const uint64_t dn = Ds[i] - lo;
+                bad[i] = (uint32_t)(dn >> 32) >= (uint32_t)(rn >> 32);
+                Ds[i + 1] = dn;
+                Rs[i + 1] = rn;
+            }
+            uint32_t any = 0u;
+#pragma unroll
+            for (int i = 0; i < K; i++) any |= bad[i];
+            if (__builtin_expect(any == 0u, 1)) {
+                D = Ds[K];
+                R = Rs[K];
+                j += (uint32_t)K;
+                sts_u32(done_a, j);
+#pragma unroll
+                for (int i = 0; i < K; i++) a[i] = b[i];
+#ifdef CCD_PROFILE
+                pc.seg[3] += K;
+#endif
+                continue;
+            }
+            // first failing symbol f: the f symbols before it were the mode; state before it, its hot entry
+            uint32_t f = K - 1;
+            uint4 hf = a[K - 1];
+            D = Ds[K - 1];
+            R = Rs[K - 1];
+#pragma unroll
+            for (int i = K - 2; i >= 0; i--) {
+                if (bad[i]) {
+                    f = (uint32_t)i;
+                    hf = a[i];
+                    D = Ds[i];
+                    R = Rs[i];
+                }
+            }
+            j += f;
+#ifdef CCD_PROFILE
+            pc.seg[3] += f;
+            c.n_redo++;
+#endif
+            single(hf);
+            break;  // re-enter through the checks above (ready count, hot entries of the new j)
         }
     }
     c.D = D;
     c.R = R;
-    c.wnext = wnext;
+    c.w0 = w0;
+    c.wpos = wpos;
+    c.wcur = wcur;
+    c.wnxt = wnxt;
+    c.wbase = wbase;
 }
 
 // Helper warp: readiness scan + publication, 32 symbols per round (lane = symbol).
@@ -969,9 +931,6 @@ __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm,
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
     uint32_t r = ord_begin, p = ord_begin;
     while (p != ord_end) {
-#ifdef CCD_PROFILE
-        pc.seg[0]++;  // rounds
-#endif
         if (r != ord_end) {
             const uint32_t jj = r + (uint32_t)lane;
             bool ok = false;
@@ -982,11 +941,6 @@ __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm,
                 r += cnt;
                 if (lane == 0) sts_u32(sm.ctrl + 4u, r);
             }
-#ifdef CCD_PROFILE
-            pc.seg[1] += cnt;
-            if (cnt == 32u) pc.seg[2]++;
-            pc.seg[3] += (int32_t)(r - p);  // ready - published
-#endif
         }
         {
             // symbols [p, done) are decoded: mode symbols left no trace, the others a tagged result word
@@ -1136,17 +1090,17 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     ds.err = 0;
     ds.slow = 0;
     ds.n_far = 0;
+    ds.n_redo = 0;
     ds.wpos = 2;
-    ds.wcur = ds.wnxt = ds.wnext = 0;
+    ds.w0 = ds.wcur = ds.wnxt = ds.wbase = 0;
     ds.D = 0;
     ds.R = ~0ull;
     if (is_coder && S.mode == 0) {
-        ds.wcur = load_word(S, lane);
-        ds.wnxt = load_word(S, 32 + lane);
-        const uint32_t w0 = __shfl_sync(0xffffffffu, ds.wcur, 0);
-        const uint32_t w1 = __shfl_sync(0xffffffffu, ds.wcur, 1);
-        ds.D = ((uint64_t)w0 << 32) | w1;
-        ds.wnext = __shfl_sync(0xffffffffu, ds.wcur, 2);
+        const uint32_t wmax = (uint32_t)S.n_words + 1u;
+        ds.wcur = coder_word(S.words, wmax, (uint32_t)lane);
+        ds.wnxt = coder_word(S.words, wmax, 32u + (uint32_t)lane);
+        ds.D = ((uint64_t)word_at(ds.wcur, ds.wnxt, 0u, 0u) << 32) | word_at(ds.wcur, ds.wnxt, 0u, 1u);
+        ds.w0 = word_at(ds.wcur, ds.wnxt, 0u, 2u);
     }
     uint32_t ord = 0;
     int chunk_ctr = 0;
@@ -1179,22 +1133,26 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
         ord += n_sym;
     }
 #ifdef CCD_PROFILE
-    // [4] coder wait, [5] coder total, [6] producers wait, [7] arm, [8] window, [9] total (kilo-cycles, lane 0 of each warp)
-    if (lane == 0 && is_helper) {
-        G.status[6] = (int)pc.seg[0];
-        G.status[7] = (int)pc.seg[1];
-        G.status[8] = (int)pc.seg[2];
-        G.status[9] = (int)(pc.seg[3] >> 4);
-        G.status[15] = (int)(pc.total >> 10);
-    } else if (lane == 0) {
-        if (is_coder) {
-            atomicAdd(&G.status[4], (int)(pc.wait >> 10));
-            atomicAdd(&G.status[5], (int)(pc.total >> 10));
-            G.status[10] = (int)pc.seg[0];
-            G.status[11] = (int)ds.n_far;
-            G.status[12] = (int)(pc.seg[2] >> 10);
-            G.status[13] = (int)pc.seg[3];  // symbols decoded in the steady loop
-            G.status[14] = (int)pc.seg[4];  // symbols decoded one at a time (coder close behind the producers)
+    // status words of the instrumented build (kilo-cycles unless stated): [4] coder wait, [5] coder total,
+    // [6..9] producers (summed over the warps): wait, ARM, window fetch + publication, total, [10] symbols outside
+    // {M-1, M, M+1}, [11] fast groups decoded again, [12] symbols decoded one at a time, [13] symbols decoded in
+    // fast groups, [14] chunks produced, [15] helper total
+    if (lane == 0) {
+        if (is_helper) {
+            G.status[15] = (int)(pc.total >> 10);
+        } else if (is_coder) {
+            G.status[4] = (int)(pc.wait >> 10);
+            G.status[5] = (int)(pc.total >> 10);
+            G.status[10] = (int)ds.n_far;
+            G.status[11] = (int)ds.n_redo;
+            G.status[12] = (int)pc.seg[4];
+            G.status[13] = (int)pc.seg[3];
+        } else {
+            atomicAdd(&G.status[6], (int)(pc.wait >> 10));
+            atomicAdd(&G.status[7], (int)(pc.arm >> 10));
+            atomicAdd(&G.status[8], (int)(pc.win >> 10));
+            atomicAdd(&G.status[9], (int)(pc.total >> 10));
+            atomicAdd(&G.status[14], (int)pc.seg[5]);
         }
     }
 #endif

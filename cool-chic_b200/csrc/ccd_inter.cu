@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ccd_detmath.h"
 #include "ccd_internal.h"
 
 namespace {
@@ -27,14 +28,25 @@ __device__ __forceinline__ void sinc_coeffs(float s, float (&c)[N]) {
     for (int k = 0; k < N; k++) {
         const float arg = __fsub_rn(s, (float)(lt + k));
         const float pa = __fmul_rn(PIf, arg);
-        const double win = cos((double)__fdiv_rn(pa, (float)N));
-        const double sc = (arg == 0.0f) ? 1.0 : sin((double)pa) / (double)pa;
+        const double win = ccdm_cos((double)__fdiv_rn(pa, (float)N));
+        const double sc = (arg == 0.0f) ? 1.0 : __ddiv_rn(ccdm_sin((double)pa), (double)pa);
         c[k] = __fmul_rn((float)win, (float)sc);
     }
 }
 
+// Reference planes: plane 0 is [h][w]; planes 1, 2 are [h >> cs][w >> cs] (cs = 1: a YUV 4:2:0 reference, read
+// through the nearest x2 up-conversion of convert_420_to_444, io/format/yuv.py:303-316, folded into the gather
+// index -- the 4:4:4 copy is never materialised).
+struct RefPlanes {
+    const float *p[3];
+};
+__device__ __forceinline__ float ref_at(const RefPlanes &r, int c, int cs, int w, int y, int x) {
+    if (c == 0 || cs == 0) return __ldg(r.p[c] + (size_t)y * w + x);
+    return __ldg(r.p[c] + (size_t)(y >> 1) * (w >> 1) + (x >> 1));
+}
+
 template <int N>
-__device__ __forceinline__ void warp_pixel(const float *__restrict__ ref, int h, int w, int gx, int gy, float fx,
+__device__ __forceinline__ void warp_pixel(const RefPlanes &ref, int cs, int h, int w, int gx, int gy, float fx,
                                            float fy, int x, int y, float (&out)[3]) {
     constexpr int lt = -(N / 2) + 1;
     const float rx = floorf(fx), ry = floorf(fy);
@@ -51,18 +63,15 @@ __device__ __forceinline__ void warp_pixel(const float *__restrict__ ref, int h,
         xs[k] = clampi((int)nx + gx, 0, w - 1);
         ys[k] = clampi((int)ny + gy, 0, h - 1);
     }
-    const size_t plane = (size_t)h * w;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        const float *p = ref + (size_t)c * plane;
         float col = 0.0f;
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            const float *row = p + (size_t)ys[i] * w;
             float line = 0.0f;
 #pragma unroll
             for (int j = 0; j < N; j++) {
-                const float t = __fmul_rn(__ldg(row + xs[j]), cx[j]);
+                const float t = __fmul_rn(ref_at(ref, c, cs, w, ys[i], xs[j]), cx[j]);
                 line = (j == 0) ? t : __fadd_rn(line, t);
             }
             const float t2 = __fmul_rn(line, cy[i]);
@@ -90,12 +99,11 @@ __device__ __forceinline__ float cubic_far(float x) {
 // grid_sample(border, align_corners=True) of the globally shifted reference: N == 2 bilinear, N == 4 bicubic.
 // Same operation order as oracle/ccoracle.c::warp_grid.
 template <int N>
-__device__ __forceinline__ void grid_pixel(const float *__restrict__ ref, int h, int w, int gx, int gy, float fx,
+__device__ __forceinline__ void grid_pixel(const RefPlanes &ref, int cs, int h, int w, int gx, int gy, float fx,
                                            float fy, int x, int y, float (&out)[3]) {
     const float sx = (float)((w - 1.0) / 2.0), sy = (float)((h - 1.0) / 2.0);
     const float g0 = __fadd_rn(lin_coord(w, x), __fdiv_rn(fx, sx)), g1 = __fadd_rn(lin_coord(h, y), __fdiv_rn(fy, sy));
     float ix = __fmul_rn(__fadd_rn(g0, 1.0f), sx), iy = __fmul_rn(__fadd_rn(g1, 1.0f), sy);
-    const size_t plane = (size_t)h * w;
     if (N == 2) {
         ix = fminf((float)(w - 1), fmaxf(ix, 0.0f));
         iy = fminf((float)(h - 1), fmaxf(iy, 0.0f));
@@ -107,11 +115,10 @@ __device__ __forceinline__ void grid_pixel(const float *__restrict__ ref, int h,
         const int ya = clampi(y0 + gy, 0, h - 1), yb = clampi((y1 < h ? y1 : h - 1) + gy, 0, h - 1);
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const float *p = ref + (size_t)c * plane;
-            const float v00 = __ldg(p + (size_t)ya * w + xa);
-            const float v01 = x1 < w ? __ldg(p + (size_t)ya * w + xb) : 0.0f;
-            const float v10 = y1 < h ? __ldg(p + (size_t)yb * w + xa) : 0.0f;
-            const float v11 = (x1 < w && y1 < h) ? __ldg(p + (size_t)yb * w + xb) : 0.0f;
+            const float v00 = ref_at(ref, c, cs, w, ya, xa);
+            const float v01 = x1 < w ? ref_at(ref, c, cs, w, ya, xb) : 0.0f;
+            const float v10 = y1 < h ? ref_at(ref, c, cs, w, yb, xa) : 0.0f;
+            const float v11 = (x1 < w && y1 < h) ? ref_at(ref, c, cs, w, yb, xb) : 0.0f;
             float r = __fmul_rn(v00, k_nw);
             r = __fmaf_rn(v01, k_ne, r);
             r = __fmaf_rn(v10, k_sw, r);
@@ -135,15 +142,13 @@ __device__ __forceinline__ void grid_pixel(const float *__restrict__ ref, int h,
         }
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            const float *p = ref + (size_t)c * plane;
             float rows[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float *q = p + (size_t)ys[i] * w;
-                float r = __fmul_rn(cx[0], __ldg(q + xs[0]));
-                r = __fmaf_rn(cx[1], __ldg(q + xs[1]), r);
-                r = __fmaf_rn(cx[2], __ldg(q + xs[2]), r);
-                r = __fmaf_rn(cx[3], __ldg(q + xs[3]), r);
+                float r = __fmul_rn(cx[0], ref_at(ref, c, cs, w, ys[i], xs[0]));
+                r = __fmaf_rn(cx[1], ref_at(ref, c, cs, w, ys[i], xs[1]), r);
+                r = __fmaf_rn(cx[2], ref_at(ref, c, cs, w, ys[i], xs[2]), r);
+                r = __fmaf_rn(cx[3], ref_at(ref, c, cs, w, ys[i], xs[3]), r);
                 rows[i] = r;
             }
             float a = __fmul_rn(cy[0], rows[0]);
@@ -156,55 +161,101 @@ __device__ __forceinline__ void grid_pixel(const float *__restrict__ ref, int h,
 }
 
 template <int N>
-__device__ __forceinline__ void predict_pixel(const float *__restrict__ ref, int h, int w, int gx, int gy, float fx,
+__device__ __forceinline__ void predict_pixel(const RefPlanes &ref, int cs, int h, int w, int gx, int gy, float fx,
                                               float fy, int x, int y, float (&out)[3]) {
     if constexpr (N <= 4)
-        grid_pixel<N>(ref, h, w, gx, gy, fx, fy, x, y, out);
+        grid_pixel<N>(ref, cs, h, w, gx, gy, fx, fy, x, y, out);
     else
-        warp_pixel<N>(ref, h, w, gx, gy, fx, fy, x, y, out);
+        warp_pixel<N>(ref, cs, h, w, gx, gy, fx, fy, x, y, out);
 }
 
+__device__ __forceinline__ float quantf(float v, float M) { return __fdiv_rn(rintf(__fmul_rn(M, v)), M); }
+__device__ __forceinline__ float clamp01f(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
+
+// One thread per pixel; a warp covers a 16 x 2 patch (lane = lx + 16 ly), so that the 2 x 2 chroma blocks of a
+// 4:2:0 frame sit inside one warp and the frame tail of decode_frame (bitstream/decode.py:191-206: round ->
+// 2 x 2 average of U, V -> clamp -> round) is done with four shuffles instead of a second pass over HBM.
+//   M == 0: out[c] = pre-rounding frame (three full planes)
+//   M  > 0: out[c] = finished frame on the k / M grid; out_420: U, V planes are [h/2][w/2]
 template <int N>
-__global__ void k_inter_predict(const float *__restrict__ residue, const float *__restrict__ motion,
-                                const float *__restrict__ ref0, const float *__restrict__ ref1, int h, int w,
-                                int is_b, int g0x, int g0y, int g1x, int g1y, float *__restrict__ out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
+__global__ void __launch_bounds__(128)
+    k_inter_predict(const float *__restrict__ residue, const float *__restrict__ motion, RefPlanes ref0, RefPlanes ref1,
+                    int ref_cs, int h, int w, int is_b, int g0x, int g0y, int g1x, int g1y, float M, int out_420,
+                    float *__restrict__ o0, float *__restrict__ o1, float *__restrict__ o2) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 32 + (wrp & 1) * 16 + (lane & 15);
+    const int py = blockIdx.y * 4 + (wrp >> 1) * 2 + (lane >> 4);
+    const bool inside = px < w && py < h;
+    const int x = px < w ? px : w - 1, y = py < h ? py : h - 1;  // every lane computes (shuffles below)
     const size_t plane = (size_t)h * w, i = (size_t)y * w + x;
     float p0[3], p1[3] = {0.0f, 0.0f, 0.0f};
-    predict_pixel<N>(ref0, h, w, g0x, g0y, motion[i], motion[plane + i], x, y, p0);
+    predict_pixel<N>(ref0, ref_cs, h, w, g0x, g0y, motion[i], motion[plane + i], x, y, p0);
     float beta = 0.0f;
     if (is_b) {
-        predict_pixel<N>(ref1, h, w, g1x, g1y, motion[2 * plane + i], motion[3 * plane + i], x, y, p1);
+        predict_pixel<N>(ref1, ref_cs, h, w, g1x, g1y, motion[2 * plane + i], motion[3 * plane + i], x, y, p1);
         beta = __fadd_rn(residue[4 * plane + i], 0.5f);
-        beta = beta < 0.0f ? 0.0f : (beta > 1.0f ? 1.0f : beta);
+        beta = clamp01f(beta);
     }
-    float alpha = __fadd_rn(residue[3 * plane + i], 0.5f);
-    alpha = alpha < 0.0f ? 0.0f : (alpha > 1.0f ? 1.0f : alpha);
+    float alpha = clamp01f(__fadd_rn(residue[3 * plane + i], 0.5f));
+    float v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         float pred = p0[c];
         if (is_b) pred = __fadd_rn(__fmul_rn(beta, pred), __fmul_rn(__fsub_rn(1.0f, beta), p1[c]));
-        out[c * plane + i] = __fadd_rn(__fmul_rn(alpha, pred), residue[c * plane + i]);
+        v[c] = __fadd_rn(__fmul_rn(alpha, pred), residue[c * plane + i]);
+    }
+    float *const outp[3] = {o0, o1, o2};
+    if (M == 0.0f) {
+        if (inside) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) outp[c][i] = v[c];
+        }
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) v[c] = quantf(v[c], M);
+    if (!out_420) {
+        if (inside) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) outp[c][i] = quantf(clamp01f(v[c]), M);
+        }
+        return;
+    }
+    if (inside) o0[i] = quantf(clamp01f(v[0]), M);
+    // 2 x 2 average of the rounded chroma samples, in the order of F.avg_pool2d's reference loop (yuv.py:295)
+    const int base = lane & ~17;
+#pragma unroll
+    for (int c = 1; c < 3; c++) {
+        float s = 0.0f;
+        s = __fadd_rn(s, __shfl_sync(0xffffffffu, v[c], base));
+        s = __fadd_rn(s, __shfl_sync(0xffffffffu, v[c], base + 1));
+        s = __fadd_rn(s, __shfl_sync(0xffffffffu, v[c], base + 16));
+        s = __fadd_rn(s, __shfl_sync(0xffffffffu, v[c], base + 17));
+        if (lane == base && px + 1 < w && py + 1 < h)
+            outp[c][(size_t)(py >> 1) * (w >> 1) + (px >> 1)] = quantf(clamp01f(__fdiv_rn(s, 4.0f)), M);
     }
 }
 
 }  // namespace
 
-int ccd_inter_launch(const float *d_residue, const float *d_motion, const float *d_ref0, const float *d_ref1, int h,
-                     int w, int is_b, const int32_t *gf, int filter_size, float *d_out, cudaStream_t st) {
-    const dim3 block(32, 8, 1), grid((w + 31) / 32, (h + 7) / 8, 1);
-#define LAUNCH(N)                                                                                              \
-    k_inter_predict<N><<<grid, block, 0, st>>>(d_residue, d_motion, d_ref0, d_ref1, h, w, is_b, gf[0], gf[1],   \
-                                               gf[2], gf[3], d_out)
-    switch (filter_size) {
-        case 2: if (h < 2 || w < 2) return -1; LAUNCH(2); break;
-        case 4: if (h < 2 || w < 2) return -1; LAUNCH(4); break;
+int ccd_inter_launch(const InterLaunch &a, cudaStream_t st) {
+    const dim3 block(128, 1, 1), grid((a.w + 31) / 32, (a.h + 3) / 4, 1);
+    RefPlanes r0, r1;
+    for (int c = 0; c < 3; c++) {
+        r0.p[c] = a.ref0[c];
+        r1.p[c] = a.ref1[c] ? a.ref1[c] : a.ref0[c];
+    }
+#define LAUNCH(N)                                                                                                  \
+    k_inter_predict<N><<<grid, block, 0, st>>>(a.residue, a.motion, r0, r1, a.ref_cs, a.h, a.w, a.is_b, a.gf[0],    \
+                                               a.gf[1], a.gf[2], a.gf[3], a.M, a.out_420, a.out[0], a.out[1], a.out[2])
+    switch (a.filter_size) {
+        case 2: if (a.h < 2 || a.w < 2) return -1; LAUNCH(2); break;
+        case 4: if (a.h < 2 || a.w < 2) return -1; LAUNCH(4); break;
         case 6: LAUNCH(6); break;
         case 8: LAUNCH(8); break;
         case 10: LAUNCH(10); break;
         case 12: LAUNCH(12); break;
+        case 14: LAUNCH(14); break;  // the largest size the 4-bit header field can carry (header.py:217)
         default: return -1;
     }
 #undef LAUNCH

@@ -122,6 +122,19 @@ int ccd_cr_noise(float *d_out, size_t first, size_t n, cudaStream_t st);
 int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, float *a, float *b, float *c,
                cudaStream_t st);
 
+int ccd_pack(const float *const planes[3], int h, int w, int cs, int bitdepth, int sample_bytes, int interleaved,
+             void *d_out, cudaStream_t st);
+
 // P/B reconstruction (ccd_inter.cu); returns -1 for an unsupported filter size
-int ccd_inter_launch(const float *d_residue, const float *d_motion, const float *d_ref0, const float *d_ref1, int h,
-                     int w, int is_b, const int32_t *gf, int filter_size, float *d_out, cudaStream_t st);
+struct InterLaunch {
+    const float *residue, *motion;  // [4|5][h][w], [2|4][h][w]
+    const float *ref0[3], *ref1[3]; // planes of the references; ref1 all null for a P frame
+    int ref_cs;                     // 1: reference chroma planes are [h/2][w/2] (4:2:0), 0: full size
+    int h, w, is_b;
+    int32_t gf[4];                  // global flow (x, y) per reference
+    int filter_size;
+    float M;                        // 0: pre-rounding output; 2^bitdepth - 1: finished frame (decode.py:191-206)
+    int out_420;                    // finished output with [h/2][w/2] chroma planes
+    float *out[3];
+};
+int ccd_inter_launch(const InterLaunch &a, cudaStream_t st);

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ccd_detmath.h"
 #include "ccd_internal.h"
 
 namespace {
@@ -527,7 +528,8 @@ __global__ void k_cr_noise(float *__restrict__ out, size_t first, size_t n) {
     const uint64_t s1 = (lcg_pow(2 * k + 1) * 18101995ULL) % m;
     const uint64_t s2 = (s1 * 16807ULL) % m;
     const double u1 = (double)s1 / (double)m, u2 = (double)s2 / (double)m;
-    out[i] = (float)(sqrt(-2 * log(u1)) * cos(2 * 3.14159265359 * u2));
+    // Box-Muller (noise.py:28-34) with the canonical log / cos of ccd_detmath.h: bit-identical to the oracle
+    out[i] = (float)__dmul_rn(__dsqrt_rn(__dmul_rn(-2.0, ccdm_log(u1))), ccdm_cos(__dmul_rn(2 * 3.14159265359, u2)));
 }
 
 __device__ __forceinline__ float quant(float v, float M) { return __fdiv_rn(rintf(__fmul_rn(M, v)), M); }
@@ -700,6 +702,92 @@ int ccd_resize_torch(const float *d_in, int c, int h, int w, float *d_out, int H
 
 int ccd_cr_noise(float *d_out, size_t first, size_t n, cudaStream_t st) {
     k_cr_noise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_out, first, n);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+// ---- output packing (io/format/yuv.py:150-162, ppm.py:160-203): finished planes -> integer samples.
+// Planar: thread = 4 consecutive samples of one plane (one float4 load, one 4- or 8-byte store).
+template <typename T>
+__global__ void k_pack_planar(const float *__restrict__ p0, const float *__restrict__ p1, const float *__restrict__ p2,
+                              size_t n0, size_t n1, float M, T *__restrict__ out) {
+    const size_t total4 = (n0 + 3) / 4 + 2 * ((n1 + 3) / 4);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t q0 = (n0 + 3) / 4, q1 = (n1 + 3) / 4;
+        const float *src;
+        size_t base, n, off;
+        if (q < q0) { src = p0; base = 0; n = n0; off = q * 4; }
+        else if (q < q0 + q1) { src = p1; base = n0; n = n1; off = (q - q0) * 4; }
+        else { src = p2; base = n0 + n1; n = n1; off = (q - q0 - q1) * 4; }
+        T v[4];
+        if (off + 4 <= n && ((reinterpret_cast<uintptr_t>(src + off) & 15) == 0)) {
+            const float4 f = __ldg(reinterpret_cast<const float4 *>(src + off));
+            v[0] = (T)rintf(__fmul_rn(f.x, M)); v[1] = (T)rintf(__fmul_rn(f.y, M));
+            v[2] = (T)rintf(__fmul_rn(f.z, M)); v[3] = (T)rintf(__fmul_rn(f.w, M));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = (off + k < n) ? (T)rintf(__fmul_rn(__ldg(src + off + k), M)) : (T)0;
+        }
+        T *dst = out + base + off;
+        if (off + 4 <= n && ((reinterpret_cast<uintptr_t>(dst) & (4 * sizeof(T) - 1)) == 0)) {
+            if (sizeof(T) == 1) *reinterpret_cast<uchar4 *>(dst) = make_uchar4(v[0], v[1], v[2], v[3]);
+            else *reinterpret_cast<ushort4 *>(dst) = make_ushort4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (off + k < n) dst[k] = v[k];
+        }
+    }
+}
+// Interleaved [H][W][3]: thread = 4 pixels = 12 samples (three float4 loads, 12 or 24 contiguous bytes out).
+template <typename T>
+__global__ void k_pack_hwc(const float *__restrict__ p0, const float *__restrict__ p1, const float *__restrict__ p2, size_t n,
+                           float M, T *__restrict__ out) {
+    const size_t nq = (n + 3) / 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x) {
+        const size_t off = q * 4;
+        T v[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const size_t i = off + k < n ? off + k : n - 1;
+            v[3 * k] = (T)rintf(__fmul_rn(__ldg(p0 + i), M));
+            v[3 * k + 1] = (T)rintf(__fmul_rn(__ldg(p1 + i), M));
+            v[3 * k + 2] = (T)rintf(__fmul_rn(__ldg(p2 + i), M));
+        }
+        T *dst = out + off * 3;
+        if (off + 4 <= n) {
+            if (sizeof(T) == 1) {
+                uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);  // off * 3 is a multiple of 12: 4-byte aligned
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    d32[k] = (uint32_t)v[4 * k] | ((uint32_t)v[4 * k + 1] << 8) | ((uint32_t)v[4 * k + 2] << 16) |
+                             ((uint32_t)v[4 * k + 3] << 24);
+            } else {
+                uint2 *d64 = reinterpret_cast<uint2 *>(dst);        // 24 bytes: 8-byte aligned
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    d64[k] = make_uint2((uint32_t)v[4 * k] | ((uint32_t)v[4 * k + 1] << 16),
+                                        (uint32_t)v[4 * k + 2] | ((uint32_t)v[4 * k + 3] << 16));
+            }
+        } else {
+            for (int k = 0; k < 12; k++)
+                if (off * 3 + k < n * 3) dst[k] = v[k];
+        }
+    }
+}
+
+int ccd_pack(const float *const planes[3], int h, int w, int cs, int bitdepth, int sample_bytes, int interleaved,
+             void *d_out, cudaStream_t st) {
+    const float M = (float)((1 << bitdepth) - 1);
+    const size_t n0 = (size_t)h * w, n1 = (size_t)(h >> cs) * (w >> cs);
+    const unsigned blocks = 148 * 8;
+    if (interleaved) {
+        if (sample_bytes == 1) k_pack_hwc<uint8_t><<<blocks, 256, 0, st>>>(planes[0], planes[1], planes[2], n0, M, (uint8_t *)d_out);
+        else k_pack_hwc<uint16_t><<<blocks, 256, 0, st>>>(planes[0], planes[1], planes[2], n0, M, (uint16_t *)d_out);
+    } else {
+        if (sample_bytes == 1) k_pack_planar<uint8_t><<<blocks, 256, 0, st>>>(planes[0], planes[1], planes[2], n0, n1, M, (uint8_t *)d_out);
+        else k_pack_planar<uint16_t><<<blocks, 256, 0, st>>>(planes[0], planes[1], planes[2], n0, n1, M, (uint16_t *)d_out);
+    }
     g_ccd_launches++;
     return (int)cudaGetLastError();
 }

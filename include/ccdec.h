@@ -155,15 +155,37 @@ int ccd_finish_frame(CcdContext *ctx, const float *d_in, int h, int w, int bitde
 
 /* P/B-frame prediction + residue (bitstream/decode.py:156-189: apply_global_translation
  * globalmotion.py:151-160, Warper.forward warp.py:294-397 in its training branch, alpha/beta
- * blending).  d_residue [4|5][H][W], d_motion [2|4][H][W]: raw synthesis outputs;
- * d_ref0/d_ref1 [3][H][W] (444).  global_flow: (x,y) per reference.  d_out [3][H][W]
- * pre-rounding frame (feed to ccd_finish_frame).  warp_filter_size 2 / 4: grid_sample bilinear /
- * bicubic (border, align_corners); 6, 8, 10, 12: windowed sinc; other even sizes return
- * CCD_ERR_UNSUPPORTED (not instantiated). */
-int ccd_inter_predict(CcdContext *ctx, const float *d_residue, const float *d_motion,
-                      const float *d_ref0, const float *d_ref1, int h, int w, int is_b,
+ * blending).  d_residue [n_res_ch][H][W], d_motion [n_mot_ch][H][W]: raw synthesis outputs; the
+ * channel counts are checked against what the path reads (P: 4 / 2, B: 5 / 4; the reference raises a
+ * shape error otherwise).  d_ref0/d_ref1 [3][H][W] (444).  global_flow: (x,y) per reference.
+ * d_out [3][H][W] pre-rounding frame.  warp_filter_size 2 / 4: grid_sample bilinear / bicubic (border,
+ * align_corners); 6, 8, 10, 12, 14: windowed sinc (14 is the largest value of the 4-bit header field,
+ * header/header.py:217); odd sizes are an argument error. */
+int ccd_inter_predict(CcdContext *ctx, const float *d_residue, int n_res_ch, const float *d_motion,
+                      int n_mot_ch, const float *d_ref0, const float *d_ref1, int h, int w, int is_b,
                       const int32_t *global_flow, int warp_filter_size, float *d_out,
                       void *cuda_stream);
+
+/* Whole reconstruction of a P/B frame in ONE kernel: the prediction above + the frame tail of
+ * ccd_finish_frame (bitstream/decode.py:156-206).  The references are given as three plane pointers
+ * each, in the layout of the frames this function (or ccd_finish_frame) produced: frame_data_type 1
+ * (yuv420): y [H][W], u, v [H/2][W/2] -- read through the nearest x2 up-conversion of
+ * convert_420_to_444 (io/format/yuv.py:303-316) folded into the gather index; otherwise three [H][W]
+ * planes.  out_planes: the finished frame in the same layout.  ref1_planes may be NULL for a P frame. */
+int ccd_reconstruct_frame(CcdContext *ctx, const float *d_residue, int n_res_ch, const float *d_motion,
+                          int n_mot_ch, const float *const ref0_planes[3],
+                          const float *const ref1_planes[3], int frame_data_type, int bitdepth, int h,
+                          int w, int is_b, const int32_t *global_flow, int warp_filter_size,
+                          float *const out_planes[3], void *cuda_stream);
+
+/* Output packing on the device (io/format/yuv.py:150-162, ppm.py:160-203, png.py:44-62): finished
+ * planes (values on the k / (2^b - 1) grid) -> integer samples round(x * (2^b - 1)), uint8 when
+ * sample_bytes == 1, little-endian uint16 when 2.  interleaved == 0: the three planes one after the
+ * other (planar YUV file order; chroma planes [H >> cs][W >> cs], cs = 1 for yuv420);
+ * interleaved == 1 (cs must be 0): pixel-interleaved [H][W][3] (PPM / PNG order).  d_out holds
+ * sample_bytes * (H*W + 2 * (H>>cs) * (W>>cs)) bytes. */
+int ccd_pack_frame(CcdContext *ctx, const float *const planes[3], int h, int w, int chroma_shift,
+                   int bitdepth, int sample_bytes, int interleaved, void *d_out, void *cuda_stream);
 
 /* Device-side evaluation of the quantised-Laplace left cumulative for testing the f64
  * exp() agreement with the host: for sc in [sc_lo, sc_hi) and every
@@ -177,7 +199,8 @@ int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *ou
 uint64_t ccd_debug_launch_count(void);
 
 /* Tuning knob: which of warps 0..14 of the entropy CTA act as ARM producers (bit i = warp i;
- * warp 15 is the range coder).  Default 0x7777: the coder keeps scheduler partition 3. */
+ * warp 14 is the coder's helper, warp 15 the range coder).  Default 0x3777: warps 3, 7, 11 stay idle so
+ * that the coder owns scheduler partition 3. */
 int ccd_debug_set_producer_mask(CcdContext *ctx, uint32_t mask);
 /* 1 (default): one fused kernel for the synthesis when the architecture allows it; 0: one kernel per
  * layer.  Both give bit-identical results (tests/test_gpu_decode.py). */
@@ -185,7 +208,8 @@ int ccd_debug_set_fused_synthesis(CcdContext *ctx, int on);
 
 /* Entropy-kernel status words of the last job of the last call: [0] error, [1] words consumed,
  * [2] slow-path symbols (outside the 31-symbol window), [3] words emitted (encode modes),
- * [4..9] cycle counters when the library is built with -DCCD_PROFILE (else 0). */
+ * [4..15] cycle / event counters when the library is built with -DCCD_PROFILE (else 0; layout in
+ * csrc/ccd_entropy.cu). */
 int ccd_debug_last_status(const CcdContext *ctx, int32_t st[16]);
 
 /* Timing of the last ccd_decode_many call on this context, measured with CUDA events on the

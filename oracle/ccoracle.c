@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "detmath.h"
+
 static const uint32_t k_scale_bits[2561] = {
 #include "scale_table.inc"
 };
@@ -966,7 +968,8 @@ int cco_resize(const float *in, int c, int h, int w, float *out, int H, int W, i
 
 /* ---- common randomness (--tune=wasserstein): component/core/noise.py:18-55 ------------------------
  * Park-Miller LCG (a = 7^5, m = 2^31 - 1, seed 18101995), two draws per sample, Box-Muller in
- * double precision with pi = 3.14159265359, rounded to fp32; one grid per latent resolution
+ * double precision with pi = 3.14159265359 (log / cos = the canonical ones of detmath.h, within 2 ulp
+ * of the libm the reference's math.log / math.cos call), rounded to fp32; one grid per latent resolution
  * (core/coolchic.py:187-191: ceil(img / 2^i)), finest first; fixed_upsampling(bicubic)
  * (upsampling.py:556-595) and a final bicubic interpolate to the image size
  * (bitstream/component/coolchic.py:180-183).  out: [n][H][W], n = latent_res_hi - latent_res_lo + 1. */
@@ -993,7 +996,7 @@ int cco_cr_noise(const CcoDesc *d, float *out) {
             double u1 = (double)seed / (double)m;
             seed = (a * seed) % m;
             double u2 = (double)seed / (double)m;
-            g[i][k] = (float)(sqrt(-2 * log(u1)) * cos(2 * pi * u2));
+            g[i][k] = (float)(sqrt(-2 * ccdm_log(u1)) * ccdm_cos(2 * pi * u2));
         }
     }
     /* cascade, coarsest first; cur holds cc planes of size ch x cw */
@@ -1215,16 +1218,17 @@ int cco_finish_frame(const float *in, int h, int w, int bitdepth, int data_type,
  * (SURVEY F5): no 1/64-pel flow quantisation; filter_size >= 6 -> windowed sinc (warp.py:226-268):
  * integer part by clamped gathers, fractional part by N taps cos(pi(s-k)/N) * sinc(s-k),
  * first along x (flow channel 0) for each of the N rows, then along y (flow channel 1).
- * Coefficients are evaluated in double precision and rounded to fp32 (the reference does it
- * in fp32: <= 1 ulp apart); products and sums are fp32, sequential, unfused.            */
+ * Coefficients are evaluated in double precision with the canonical sin / cos of detmath.h (exactly
+ * reproducible on the GPU) and rounded to fp32 (the reference does it in fp32 with its platform's libm:
+ * <= 1 ulp apart); products and sums are fp32, sequential, unfused.            */
 static void sinc_coeffs(float s, int n, float *c) {
     const float PIf = 3.14159265358979323846f;
     int lt = -(n / 2) + 1;
     for (int k = 0; k < n; k++) {
         float arg = s - (float)(lt + k);
         float pa = PIf * arg;
-        double win = cos((double)(pa / (float)n));
-        double sc = (arg == 0.0f) ? 1.0 : sin((double)pa) / (double)pa;
+        double win = ccdm_cos((double)(pa / (float)n));
+        double sc = (arg == 0.0f) ? 1.0 : ccdm_sin((double)pa) / (double)pa;
         c[k] = (float)win * (float)sc;
     }
 }

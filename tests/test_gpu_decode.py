@@ -243,11 +243,11 @@ def test_full_size_round_trip(ctx, oracle, seed_stream, hw, lr):
 
 # ------------------------------------------------------------------------------------------
 # P/B frames
-TOL_INTER = 1e-6  # sinc coefficients go through device / host double-precision cos, sin
+# sinc coefficients: canonical double-precision sin / cos shared by the oracle and the device (detmath): bit-exact
 
 
 @pytest.mark.parametrize("is_b,fs", [(False, 8), (True, 8), (True, 6), (False, 12), (False, 2), (True, 2), (False, 4),
-                                      (True, 4)])
+                                      (True, 4), (False, 14), (True, 10)])
 def test_inter_predict_vs_oracle(ctx, oracle, is_b, fs):
     import torch
 
@@ -268,7 +268,7 @@ def test_inter_predict_vs_oracle(ctx, oracle, is_b, fs):
         refs.append(FrameData(8, "rgb", torch.from_numpy(ref1[None]).cuda()))
     got = ctx.inter_predict(torch.from_numpy(residue[None]).cuda(), torch.from_numpy(motion[None]).cuda(), refs, is_b,
                             "rgb", gf, fs)
-    assert np.abs(got[0].cpu().numpy() - want).max() <= TOL_INTER
+    assert np.array_equal(got[0].cpu().numpy(), want)
 
 
 def test_unsupported_warp_is_an_error_not_a_fallback(ctx):
@@ -278,9 +278,95 @@ def test_unsupported_warp_is_an_error_not_a_fallback(ctx):
     from coolchic_b200.io import FrameData
 
     z = torch.zeros((1, 4, 8, 8), device="cuda")
+    ref = [FrameData(8, "rgb", z[:, :3].contiguous())]
+    with pytest.raises(_native.CcdError) as e:  # 16 taps cannot be signalled by the 4-bit header field: not built
+        ctx.inter_predict(z, z[:, :2].contiguous(), ref, False, "rgb", [0, 0], 16)
+    assert e.value.code == -4  # CCD_ERR_UNSUPPORTED
     with pytest.raises(_native.CcdError) as e:
-        ctx.inter_predict(z, z[:, :2].contiguous(), [FrameData(8, "rgb", z[:, :3].contiguous())], False, "rgb", [0, 0], 14)
-    assert e.value.code == -4  # CCD_ERR_UNSUPPORTED: sinc-14 is not instantiated
+        ctx.inter_predict(z, z[:, :2].contiguous(), ref, False, "rgb", [0, 0], 7)
+    assert e.value.code == -1  # CCD_ERR_ARG: odd filter size
+    # shape errors are raised before any pointer reaches a kernel (the reference raises on them too)
+    with pytest.raises(ValueError):  # P-frame residue with 3 channels
+        ctx.inter_predict(z[:, :3].contiguous(), z[:, :2].contiguous(), ref, False, "rgb", [0, 0], 8)
+    with pytest.raises(ValueError):  # B frame with a 2-channel motion field
+        ctx.inter_predict(torch.zeros((1, 5, 8, 8), device="cuda"), z[:, :2].contiguous(), ref + ref, True, "rgb",
+                          [0, 0, 0, 0], 8)
+    with pytest.raises(ValueError):  # reference of another size
+        ctx.inter_predict(z, z[:, :2].contiguous(), [FrameData(8, "rgb", torch.zeros((1, 3, 8, 10), device="cuda"))],
+                          False, "rgb", [0, 0], 8)
+    with pytest.raises(ValueError):  # B frame, one reference
+        ctx.reconstruct_frame(torch.zeros((1, 5, 8, 8), device="cuda"), z, ref, True, "rgb", 8, [0, 0, 0, 0], 8)
+
+
+@pytest.mark.parametrize("fmt,is_b,fs,bitdepth", [("yuv420", True, 8, 8), ("yuv420", False, 6, 10), ("yuv444", True, 4, 10),
+                                                   ("rgb", False, 2, 8), ("yuv420", True, 2, 8)])
+def test_reconstruct_frame_vs_oracle(ctx, oracle, fmt, is_b, fs, bitdepth):
+    """The one-kernel P/B reconstruction (4:2:0 references read in place, fused frame tail) against the oracle's
+    convert_420_to_444 -> inter_predict -> finish_frame sequence: identical samples."""
+    import torch
+
+    from coolchic_b200.io import FrameData
+
+    rng = np.random.default_rng(23)
+    h, w = 46, 72
+    M = 2**bitdepth - 1
+    residue = rng.normal(0, 0.3, size=(5 if is_b else 4, h, w)).astype(np.float32)
+    motion = rng.normal(0, 2.5, size=(4 if is_b else 2, h, w)).astype(np.float32)
+
+    def make_ref():
+        if fmt == "yuv420":
+            return {"y": (rng.integers(0, M + 1, size=(h, w)) / M).astype(np.float32),
+                    "u": (rng.integers(0, M + 1, size=(h // 2, w // 2)) / M).astype(np.float32),
+                    "v": (rng.integers(0, M + 1, size=(h // 2, w // 2)) / M).astype(np.float32)}
+        return (rng.integers(0, M + 1, size=(3, h, w)) / M).astype(np.float32)
+
+    refs = [make_ref() for _ in range(2 if is_b else 1)]
+
+    def to444(r):
+        if fmt != "yuv420":
+            return r
+        up = lambda p: np.repeat(np.repeat(p, 2, axis=0), 2, axis=1)  # noqa: E731
+        return np.stack([r["y"], up(r["u"]), up(r["v"])])
+
+    gf = [2, -3, -1, 4] if is_b else [-4, 1]
+    pre = oracle.inter_predict(residue, motion, to444(refs[0]), to444(refs[1]) if is_b else None, gf, fs)
+    want = oracle.finish_frame(pre, bitdepth, fmt)
+
+    def to_fd(r):
+        if fmt == "yuv420":
+            return FrameData(bitdepth, fmt, {k: torch.from_numpy(v[None, None]).cuda() for k, v in r.items()})
+        return FrameData(bitdepth, fmt, torch.from_numpy(r[None]).cuda())
+
+    got = ctx.reconstruct_frame(torch.from_numpy(residue[None]).cuda(), torch.from_numpy(motion[None]).cuda(),
+                                [to_fd(r) for r in refs], is_b, fmt, bitdepth, gf, fs)
+    if fmt == "yuv420":
+        for k in "yuv":
+            assert np.array_equal(got[k][0, 0].cpu().numpy(), want[k]), k
+    else:
+        assert np.array_equal(got[0].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("fmt,bitdepth,hw", [("rgb", 8, (37, 53)), ("yuv420", 8, (36, 50)), ("yuv420", 10, (36, 50)),
+                                             ("yuv444", 10, (33, 47)), ("rgb", 16, (5, 3))])
+def test_pack_frame(ctx, fmt, bitdepth, hw):
+    """Device-side output packing (f3): planar and pixel-interleaved integer samples equal numpy's."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    h, w = hw
+    M = 2**bitdepth - 1
+    if fmt == "yuv420":
+        planes = [rng.integers(0, M + 1, size=s) for s in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
+        data = {k: torch.from_numpy((p / M).astype(np.float32)[None, None]).cuda() for k, p in zip("yuv", planes)}
+    else:
+        planes = list(rng.integers(0, M + 1, size=(3, h, w)))
+        data = torch.from_numpy((np.stack(planes) / M).astype(np.float32)[None]).cuda()
+    dt = np.uint8 if bitdepth <= 8 else np.uint16
+    got = ctx.pack_frame(data, bitdepth, fmt).cpu().numpy().view(dt)
+    assert np.array_equal(got, np.concatenate([p.reshape(-1) for p in planes]).astype(dt))
+    if fmt != "yuv420":
+        got = ctx.pack_frame(data, bitdepth, fmt, interleaved=True).cpu().numpy().view(dt)
+        assert np.array_equal(got, np.stack(planes).transpose(1, 2, 0).reshape(-1).astype(dt))
 
 
 @pytest.mark.parametrize("name,fmt", [("gop5_64x96_yuv420", "yuv420"), ("gop3_40x56_rgb", "rgb"),
@@ -312,7 +398,9 @@ def test_gop_decode_video(ctx, name, fmt, tmp_path):
             assert np.abs(a - b).max() <= 1
             bad += int((a != b).sum())
             tot += a.size
-    assert bad <= max(4, tot // 2000)  # rounding ties only
+    # the oracle itself differs from the reference in at most 1 sample (sinc-6 fixture, tests/test_oracle.py):
+    # rounding ties of the fp32 coefficient evaluation; the device equals the oracle
+    assert bad <= (1 if name.endswith("sinc6") else 0)
     if fmt == "yuv420":
         h, w = frames["0"].data["y"].shape[-2:]
         assert os.path.getsize(out) == n * (h * w * 3 // 2)  # planar frames appended in display order
@@ -346,11 +434,12 @@ def test_gop_1080p_yuv420_properties(ctx, seed_stream):
 # ----------------------------------------------------------------------------------------------
 # optional branches of the synthesis input / output
 @pytest.mark.parametrize("name", ["img_48x72_rgb_common_randomness", "img_50x70_rgb_final_bicubic",
-                                  "img_44x60_yuv420_final_bilinear", "img_40x56_yuv444_10bit_arm24"])
+                                  "img_44x60_yuv420_final_bilinear", "img_40x56_yuv444_10bit_arm24",
+                                  "img_48x64_rgb_arm8_1hidden"])
 def test_optional_synthesis_branches(ctx, oracle, name):
     """Common randomness and bilinear / bicubic final resize on the device: raw synthesis output vs the
-    oracle (tolerance: device f64 log / cos are not glibc's; everything else is the same fp32 sequence),
-    decoded image vs the UNMODIFIED reference's (oracle/gen_golden_modes.py)."""
+    oracle (same fp32 sequence, Box-Muller through the canonical log / cos: bit-exact), decoded image vs the
+    UNMODIFIED reference's (oracle/gen_golden_modes.py)."""
     from coolchic_b200 import synth
     from coolchic_b200._desc import desc_from_header
     from coolchic_b200.bitstream.decode import decode_video
@@ -363,7 +452,7 @@ def test_optional_synthesis_branches(ctx, oracle, name):
     nn = oracle.decode_nn(desc, nn_bytes)
     lat, _ = oracle.decode_latents(desc, nn, payload)
     want = oracle.synthesize(desc, nn, lat)
-    assert np.abs(raw - want).max() <= 1e-6
+    assert np.array_equal(raw, want)
     gold = np.load(os.path.join(GOLDEN, name + ".npz"))
     fd = decode_video(path, None)["0"]
     M = 2**fd.bitdepth - 1

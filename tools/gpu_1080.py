@@ -23,7 +23,10 @@ nn = _native.decode_nn(d, nnb)
 print("symbols", d.n_symbols(), "payload", len(lb), "bpp %.3f" % (len(lb) * 8 / (1080 * 1920)))
 for it in range(3):
     out = ctx.decode_latents(d, nn, lb); torch.cuda.synchronize()
-    print(ctx.last_timing(), ctx.last_status())
+    st = ctx.last_status()
+    print(ctx.last_timing(), st[:4])
+    if any(st[4:]):
+        print("  prof kcyc: coder wait %d total %d | producers wait %d arm %d win %d total %d | far %d redo-groups %d singles %d fast %d chunks %d | helper total %d" % tuple(st[4:16]))
 print("round trip ok:", torch.equal(out, lat))
 l = lat.cpu().numpy().astype(int); off = 0
 for g in range(d.n_grids - 1, -1, -1):
