@@ -777,15 +777,76 @@ __device__ __noinline__ FarOut coder_far(uint32_t wrow, uint32_t meta_slot, cons
     return o;
 }
 
-#ifndef CCD_FAST_K
-#define CCD_FAST_K 4  // symbols per tier-1 group
+// TIER 2 as a function: symbol j, state and word queue by value in, by value out (registers; a reference into the
+// kernel's state would put it in local memory).  A taken branch costs the coder warp ~40 cycles (instruction
+// refetch: no other warp on its scheduler hides it), so the steady loop below is straight-line code whose only
+// taken branches are this call / return and one back-edge per 2 K symbols.
+struct T2Out {
+    uint32_t d_lo, d_hi, r_lo, r_hi, w0, wpos;
+    uint32_t flags;  // 2: outside the window (exact search), 4: desynchronised, 8: far (instrumented build)
+};
+__device__ __noinline__ T2Out coder_tier2(uint32_t res_a, uint32_t win_a, uint32_t meta_a, const float *__restrict__ scale_tab,
+                                          uint32_t ring_mask, int lane, uint32_t j, const uint4 h, uint64_t D, uint64_t R,
+                                          uint32_t w0, uint32_t wpos, const uint32_t wcur, const uint32_t wnxt,
+                                          const uint32_t wbase) {
+    const uint64_t D0 = D, R0 = R;
+    const uint32_t w00 = w0, wp0 = wpos;
+#ifdef CCD_T2_WINDOW
+    // variant: no select tree, straight to the lane-parallel window search (compact code)
+    FastOut f;
+    f.far = 1u;
+    f.t = 0u;
+    (void)h;
+#else
+    const FastOut f = fast_step(D, R, w0, wpos, wcur, wnxt, wbase, h);
 #endif
+    uint32_t rw = f.t, flags = 0u;
+    if (f.far) {
+        const uint32_t slot = j & ring_mask;
+        const uint64_t scale = R0 >> 24;
+        const FarOut o = coder_far(win_a + slot * (CCD_WIN * 4), meta_a + slot * 16u, scale_tab, lane, scale, D0);
+        uint64_t Dn = D0 - o.lo, Rn = o.hi - o.lo;
+        w0 = w00;
+        wpos = wp0;
+        if ((Rn >> 32) == 0) {
+            Dn = (Dn << 32) | w0;
+            Rn <<= 32;
+            wpos++;
+            w0 = word_at(wcur, wnxt, wbase, wpos);
+        }
+        D = Dn;
+        R = Rn;
+        rw = o.rw;
+#ifdef CCD_T2_WINDOW
+        flags = o.flags;
+#else
+        flags = o.flags | 8u;
+#endif
+    }
+    // shared-memory stores of one warp are performed in program order: this word is visible before the `done`
+    // store that follows it
+    if (rw != (uint32_t)CCD_WIN_HALF) sts_u32(res_a + (j & ring_mask) * 4u, res_tag(j) | rw);
+    T2Out r;
+    r.d_lo = (uint32_t)D;
+    r.d_hi = (uint32_t)(D >> 32);
+    r.r_lo = (uint32_t)R;
+    r.r_hi = (uint32_t)(R >> 32);
+    r.w0 = w0;
+    r.wpos = wpos;
+    r.flags = flags;
+    return r;
+}
 
 __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
                                            int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
                                            ProfCounters &pc) {
-    constexpr int K = CCD_FAST_K;
-    static_assert(K >= 2 && K <= CCD_HOT_MIRROR, "group size");
+#ifdef CCD_ONE_BLOCK
+#define CCD_STEADY_MIN 2u
+#else
+#define CCD_STEADY_MIN 3u
+#endif
+    constexpr uint32_t K = 4;  // symbols per straight-line block
+    static_assert(K <= CCD_HOT_MIRROR, "block size");
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
     const uint32_t ready_a = sm.ctrl + 4u, done_a = sm.ctrl + 8u;
     const uint32_t *__restrict__ words = S.words;
@@ -794,48 +855,111 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     uint32_t w0 = c.w0, wpos = c.wpos, wcur = c.wcur, wnxt = c.wnxt, wbase = c.wbase;
     uint32_t j = ord_begin;
     uint32_t limit = ord_begin;  // symbols < limit have their window in the ring
+    uint32_t o;
+    uint4 a0, a1, a2, a3, b0, b1, b2, b3;
     auto refresh = [&]() {
         const uint32_t r = lds_u32(ready_a);
         limit = ((int32_t)(r - ord_end) > 0) ? ord_end : r;
     };
-    // TIER 2: symbol j, its hot entry in hh; publishes `done`
-    auto single = [&](const uint4 hh) {
-        if (wpos - wbase >= 32u) {  // the lane-held words move on
-            wcur = wnxt;
-            wbase += 32u;
-            wnxt = coder_word(words, wmax, wbase + 32u + (uint32_t)lane);
-        }
-        const uint64_t D0 = D, R0 = R;
-        const uint32_t w00 = w0, wp0 = wpos;
-        const FastOut f = fast_step(D, R, w0, wpos, wcur, wnxt, wbase, hh);
-        uint32_t rw = f.t;
-        if (f.far) {
-            const uint32_t slot = j & ring_mask;
-            const uint64_t scale = R0 >> 24;
-            const FarOut o = coder_far(sm.win + slot * (CCD_WIN * 4), sm.meta + slot * 16u, scale_tab, lane, scale, D0);
-            uint64_t Dn = D0 - o.lo, Rn = o.hi - o.lo;
-            w0 = w00;
-            wpos = wp0;
-            if ((Rn >> 32) == 0) {
-                Dn = (Dn << 32) | w0;
-                Rn <<= 32;
-                wpos++;
-                w0 = word_at(wcur, wnxt, wbase, wpos);
-            }
-            D = Dn;
-            R = Rn;
-            rw = o.rw;
-            if (o.flags & 2u) c.slow++;
-            if (o.flags & 4u) c.err = CCD_ERR_DESYNC;
-#ifdef CCD_PROFILE
-            c.n_far++;
-#endif
-        }
-        // shared-memory stores of one warp are performed in program order: the word is visible before `done`
-        if (rw != (uint32_t)CCD_WIN_HALF) sts_u32(sm.res + (j & ring_mask) * 4u, res_tag(j) | rw);
-        j++;
-        sts_u32(done_a, j);
+    auto advance_words = [&]() {  // the lane-held words move on (at most K words are consumed between two calls)
+        wcur = wnxt;
+        wbase += 32u;
+        wnxt = coder_word(words, wmax, wbase + 32u + (uint32_t)lane);
     };
+    auto note_flags = [&](uint32_t fl) {  // rare: touches the (local-memory) decoder state
+        if (fl & 2u) c.slow++;
+        if (fl & 4u) c.err = CCD_ERR_DESYNC;
+#ifdef CCD_PROFILE
+        c.n_far++;
+#endif
+    };
+// tier 2 through the function (two more taken branches: used off the steady path only)
+#define CCD_TIER2(JJ, H)                                                                                              \
+    do {                                                                                                              \
+        const T2Out r_ = coder_tier2(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, (JJ), (H), D, R, w0, wpos, wcur, \
+                                     wnxt, wbase);                                                                    \
+        D = ((uint64_t)r_.d_hi << 32) | r_.d_lo;                                                                      \
+        R = ((uint64_t)r_.r_hi << 32) | r_.r_lo;                                                                      \
+        w0 = r_.w0;                                                                                                   \
+        wpos = r_.wpos;                                                                                               \
+        if (__builtin_expect(r_.flags != 0u, 0)) note_flags(r_.flags);                                                \
+    } while (0)
+// tier 2 inline (the first failing symbol of a block): three candidates + renormalisation by selects, far by call
+#define CCD_T2_INLINE(JJ, H)                                                                                          \
+    {                                                                                                                 \
+        const uint64_t D0_ = D, R0_ = R;                                                                              \
+        const uint32_t w00_ = w0, wp0_ = wpos;                                                                        \
+        const FastOut f_ = fast_step(D, R, w0, wpos, wcur, wnxt, wbase, (H));                                         \
+        uint32_t rw_ = f_.t;                                                                                          \
+        if (__builtin_expect(f_.far != 0u, 0)) {                                                                      \
+            const uint32_t slot_ = (JJ) & ring_mask;                                                                  \
+            const FarOut o_ = coder_far(sm.win + slot_ * (CCD_WIN * 4), sm.meta + slot_ * 16u, scale_tab, lane, R0_ >> 24, D0_); \
+            uint64_t Dn_ = D0_ - o_.lo, Rn_ = o_.hi - o_.lo;                                                          \
+            w0 = w00_;                                                                                                \
+            wpos = wp0_;                                                                                              \
+            if ((Rn_ >> 32) == 0) {                                                                                   \
+                Dn_ = (Dn_ << 32) | w0;                                                                               \
+                Rn_ <<= 32;                                                                                           \
+                wpos++;                                                                                               \
+                w0 = word_at(wcur, wnxt, wbase, wpos);                                                                \
+            }                                                                                                         \
+            D = Dn_;                                                                                                  \
+            R = Rn_;                                                                                                  \
+            rw_ = o_.rw;                                                                                              \
+            note_flags(o_.flags | 8u);                                                                                \
+        }                                                                                                             \
+        if (rw_ != (uint32_t)CCD_WIN_HALF) sts_u32(sm.res + ((JJ) & ring_mask) * 4u, res_tag(JJ) | rw_);              \
+    }
+// K tier-1 steps on entries H0..H3; bad_i != 0 when symbol i is not "the mode, no renormalisation"
+#define CCD_BLOCK(H0, H1, H2, H3)                                                                                     \
+    uint64_t Ds1, Rs1, Ds2, Rs2, Ds3, Rs3, Ds4, Rs4;                                                                  \
+    uint32_t bad0, bad1, bad2, bad3;                                                                                  \
+    {                                                                                                                 \
+        uint64_t sc_ = R >> 24;                                                                                       \
+        Rs1 = sc_ * ((H0).z - (H0).y);                                                                                \
+        Ds1 = D - sc_ * (H0).y;                                                                                       \
+        bad0 = (uint32_t)(Ds1 >> 32) >= (uint32_t)(Rs1 >> 32);                                                        \
+        sc_ = Rs1 >> 24;                                                                                              \
+        Rs2 = sc_ * ((H1).z - (H1).y);                                                                                \
+        Ds2 = Ds1 - sc_ * (H1).y;                                                                                     \
+        bad1 = (uint32_t)(Ds2 >> 32) >= (uint32_t)(Rs2 >> 32);                                                        \
+        sc_ = Rs2 >> 24;                                                                                              \
+        Rs3 = sc_ * ((H2).z - (H2).y);                                                                                \
+        Ds3 = Ds2 - sc_ * (H2).y;                                                                                     \
+        bad2 = (uint32_t)(Ds3 >> 32) >= (uint32_t)(Rs3 >> 32);                                                        \
+        sc_ = Rs3 >> 24;                                                                                              \
+        Rs4 = sc_ * ((H3).z - (H3).y);                                                                                \
+        Ds4 = Ds3 - sc_ * (H3).y;                                                                                     \
+        bad3 = (uint32_t)(Ds4 >> 32) >= (uint32_t)(Rs4 >> 32);                                                        \
+    }
+// first failing symbol f of the block: state before it by selects, the hot entries of the K symbols after it are
+// requested (their latency hides behind tier 2), tier 2 through the function, back to the top
+#define CCD_RECOVER(H0, H1, H2, H3)                                                                                   \
+    {                                                                                                                 \
+        uint32_t f_ = 3u;                                                                                             \
+        uint4 hf_ = (H3);                                                                                             \
+        uint64_t Df_ = Ds3, Rf_ = Rs3;                                                                                \
+        if (bad2) { f_ = 2u; hf_ = (H2); Df_ = Ds2; Rf_ = Rs2; }                                                      \
+        if (bad1) { f_ = 1u; hf_ = (H1); Df_ = Ds1; Rf_ = Rs1; }                                                      \
+        if (bad0) { f_ = 0u; hf_ = (H0); Df_ = D; Rf_ = R; }                                                          \
+        D = Df_;                                                                                                      \
+        R = Rf_;                                                                                                      \
+        j += f_;                                                                                                      \
+        o = sm.hot + ((j + 1u) & ring_mask) * 16u;                                                                    \
+        a0 = lds_v4(o);                                                                                               \
+        a1 = lds_v4(o + 16u);                                                                                         \
+        a2 = lds_v4(o + 32u);                                                                                         \
+        a3 = lds_v4(o + 48u);                                                                                         \
+        CCD_T2_INLINE(j, hf_)                                                                                         \
+        j++;                                                                                                          \
+        sts_u32(done_a, j);                                                                                           \
+        PROF_COUNT_RECOVER(f_);                                                                                       \
+    }
+#ifdef CCD_PROFILE
+#define PROF_COUNT_RECOVER(F) do { pc.seg[3] += (F); c.n_redo++; } while (0)
+#else
+#define PROF_COUNT_RECOVER(F)
+#endif
     while (j != ord_end) {
         if ((int32_t)(limit - j) <= 0) {
             PROF_T(t0);
@@ -844,78 +968,117 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
             } while ((int32_t)(limit - j) <= 0);
             PROF_ADD(pc.wait, t0);
         }
-        if ((int32_t)(limit - j) < 2 * K) {
-            // the coder is close behind the producers (small grids, where the ARM latency bounds the stream)
-            single(lds_v4(sm.hot + (j & ring_mask) * 16u));
+        if (wpos - wbase >= 32u) advance_words();
+        if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K) && (int32_t)(limit - j) >= (int32_t)K) {
+            // fewer symbols ready than the steady loop wants (short diagonals): one block, entries requested now
+            o = sm.hot + (j & ring_mask) * 16u;
+            a0 = lds_v4(o);
+            a1 = lds_v4(o + 16u);
+            a2 = lds_v4(o + 32u);
+            a3 = lds_v4(o + 48u);
+            CCD_BLOCK(a0, a1, a2, a3)
+            if ((bad0 | bad1 | bad2 | bad3) != 0u) {
+                CCD_RECOVER(a0, a1, a2, a3)
+            } else {
+                D = Ds4;
+                R = Rs4;
+                j += K;
+                sts_u32(done_a, j);
+#ifdef CCD_PROFILE
+                pc.seg[3] += K;
+#endif
+            }
+            continue;
+        }
+        if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) {
+            // the coder is close behind the producers (small grids, where the ARM latency bounds the stream);
+            // (same bound as the steady loop's: between the two nothing would be decoded)
+            const uint4 hh = lds_v4(sm.hot + (j & ring_mask) * 16u);
+            {
+                const uint64_t scale_ = R >> 24;
+                const uint64_t lo_ = scale_ * hh.y, rn_ = scale_ * (hh.z - hh.y);
+                const uint64_t dn_ = D - lo_;
+                if ((uint32_t)(dn_ >> 32) < (uint32_t)(rn_ >> 32)) {  // tier 1
+                    D = dn_;
+                    R = rn_;
+                } else {
+                    CCD_TIER2(j, hh);
+                }
+            }
+            j++;
+            sts_u32(done_a, j);
 #ifdef CCD_PROFILE
             pc.seg[4]++;
 #endif
             continue;
         }
-        // ---- steady state: tier-1 groups
-        uint32_t o = sm.hot + (j & ring_mask) * 16u;  // (the ring's first entries are mirrored behind its end)
-        uint4 a[K], b[K];
-#pragma unroll
-        for (int i = 0; i < K; i++) a[i] = lds_v4(o + 16u * i);
+        // ---- steady state: blocks of K symbols, branch-free (tier 1 on every symbol, flags and intermediate states
+        // kept in registers), ONE branch per block; two blocks per iteration with the roles of the two sets of hot
+        // entries swapped (no copies).  A far taken branch costs this warp ~40 cycles (instruction refetch; nothing
+        // else runs on its scheduler), a short forward skip ~11.
+        o = sm.hot + (j & ring_mask) * 16u;  // (the ring's first entries are mirrored behind its end)
+        a0 = lds_v4(o);
+        a1 = lds_v4(o + 16u);
+        a2 = lds_v4(o + 32u);
+        a3 = lds_v4(o + 48u);
         while (true) {
-            if ((int32_t)(limit - j) < 2 * K) {
+            // (K entries in a0..a3 valid for j; 2 K more must be ready for the two prefetches of this iteration)
+            if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) {
                 refresh();
-                if ((int32_t)(limit - j) < 2 * K) break;
+                if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) break;
             }
+            if (wpos - wbase >= 32u) advance_words();
             o = sm.hot + ((j + K) & ring_mask) * 16u;
-#pragma unroll
-            for (int i = 0; i < K; i++) b[i] = lds_v4(o + 16u * i);
-            uint64_t Ds[K + 1], Rs[K + 1];
-            uint32_t bad[K];
-            Ds[0] = D;
-            Rs[0] = R;
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                const uint64_t scale = Rs[i] >> 24;
-                const uint64_t lo = scale * a[i].y, rn = scale * (a[i].z - a[i].y);
-                const uint64_t dn = Ds[i] - lo;
-                bad[i] = (uint32_t)(dn >> 32) >= (uint32_t)(rn >> 32);
-                Ds[i + 1] = dn;
-                Rs[i + 1] = rn;
-            }
-            uint32_t any = 0u;
-#pragma unroll
-            for (int i = 0; i < K; i++) any |= bad[i];
-            if (__builtin_expect(any == 0u, 1)) {
-                D = Ds[K];
-                R = Rs[K];
-                j += (uint32_t)K;
-                sts_u32(done_a, j);
-#pragma unroll
-                for (int i = 0; i < K; i++) a[i] = b[i];
-#ifdef CCD_PROFILE
-                pc.seg[3] += K;
-#endif
-                continue;
-            }
-            // first failing symbol f: the f symbols before it were the mode; state before it, its hot entry
-            uint32_t f = K - 1;
-            uint4 hf = a[K - 1];
-            D = Ds[K - 1];
-            R = Rs[K - 1];
-#pragma unroll
-            for (int i = K - 2; i >= 0; i--) {
-                if (bad[i]) {
-                    f = (uint32_t)i;
-                    hf = a[i];
-                    D = Ds[i];
-                    R = Rs[i];
+            b0 = lds_v4(o);
+            b1 = lds_v4(o + 16u);
+            b2 = lds_v4(o + 32u);
+            b3 = lds_v4(o + 48u);
+            {
+                CCD_BLOCK(a0, a1, a2, a3)
+                if ((bad0 | bad1 | bad2 | bad3) != 0u) {
+                    CCD_RECOVER(a0, a1, a2, a3)
+                    continue;
                 }
+                D = Ds4;
+                R = Rs4;
             }
-            j += f;
-#ifdef CCD_PROFILE
-            pc.seg[3] += f;
-            c.n_redo++;
+#ifdef CCD_ONE_BLOCK
+            // variant: one block per iteration (the steady loop needs 2 K ready symbols instead of 3 K), entries copied
+            j += K;
+            sts_u32(done_a, j);
+            a0 = b0;
+            a1 = b1;
+            a2 = b2;
+            a3 = b3;
+            continue;
 #endif
-            single(hf);
-            break;  // re-enter through the checks above (ready count, hot entries of the new j)
+            sts_u32(done_a, j + K);  // every lane stores the same word: no predicate on the hot path
+            o = sm.hot + ((j + 2u * K) & ring_mask) * 16u;
+            a0 = lds_v4(o);
+            a1 = lds_v4(o + 16u);
+            a2 = lds_v4(o + 32u);
+            a3 = lds_v4(o + 48u);
+            {
+                CCD_BLOCK(b0, b1, b2, b3)
+                if ((bad0 | bad1 | bad2 | bad3) != 0u) {
+                    j += K;
+                    CCD_RECOVER(b0, b1, b2, b3)
+                    continue;
+                }
+                D = Ds4;
+                R = Rs4;
+            }
+            j += 2u * K;
+            sts_u32(done_a, j);
+#ifdef CCD_PROFILE
+            pc.seg[3] += 2 * K;
+#endif
         }
     }
+#undef CCD_BLOCK
+#undef CCD_RECOVER
+#undef CCD_T2_INLINE
+#undef CCD_TIER2
     c.D = D;
     c.R = R;
     c.w0 = w0;
