@@ -43,6 +43,10 @@ class CcdJob(ctypes.Structure):
         ("d_out", ctypes.c_void_p),
         ("d_latents", ctypes.c_void_p),
         ("status", ctypes.c_int32),
+        ("finish_bitdepth", ctypes.c_int32),
+        ("finish_type", ctypes.c_int32),
+        ("d_out_u", ctypes.c_void_p),
+        ("d_out_v", ctypes.c_void_p),
     ]
 
 
@@ -177,22 +181,38 @@ class Context:
 
     # ---- whole Cool-chic(s) -----------------------------------------------------------
     def decode_many(self, descs: Sequence[CcdCoolChicDesc], nn_bytes: Sequence[bytes],
-                    latent_bytes: Sequence[bytes], want_latents: bool = False):
+                    latent_bytes: Sequence[bytes], want_latents: bool = False, finish=None):
         """Decode n independent Cool-chics concurrently.  Returns (outputs, latents) where
-        outputs[i] is a float32 CUDA tensor [1, C, H, W] (raw synthesis output)."""
+        outputs[i] is a float32 CUDA tensor [1, C, H, W] (raw synthesis output).
+        ``finish[i] = (bitdepth, frame_data_type)`` (or None) asks for decode_frame's frame tail fused into the
+        synthesis kernel: outputs[i] is then the FINISHED frame in FrameData layout ([1, 3, H, W], or the
+        y / u / v dictionary for yuv420)."""
         n = len(descs)
         jobs = (CcdJob * n)()
         outs, lats = [], []
         for i in range(n):
             d = descs[i]
-            out = torch.empty((1, d.n_out_channels, d.img_h, d.img_w), dtype=torch.float32, device=self.torch_device)
-            outs.append(out)
+            fin = finish[i] if finish is not None else None
             jobs[i].desc = ctypes.pointer(d)
             jobs[i].nn_bytes = nn_bytes[i]
             jobs[i].nn_nbytes = len(nn_bytes[i])
             jobs[i].latent_bytes = latent_bytes[i]
             jobs[i].latent_nbytes = len(latent_bytes[i])
-            jobs[i].d_out = out.data_ptr()
+            if fin is not None and fin[1] == "yuv420":
+                h, w = d.img_h, d.img_w
+                out = {"y": torch.empty((1, 1, h, w), dtype=torch.float32, device=self.torch_device),
+                       "u": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=self.torch_device),
+                       "v": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=self.torch_device)}
+                jobs[i].d_out = out["y"].data_ptr()
+                jobs[i].d_out_u = out["u"].data_ptr()
+                jobs[i].d_out_v = out["v"].data_ptr()
+            else:
+                out = torch.empty((1, d.n_out_channels, d.img_h, d.img_w), dtype=torch.float32, device=self.torch_device)
+                jobs[i].d_out = out.data_ptr()
+            if fin is not None:
+                jobs[i].finish_bitdepth = int(fin[0])
+                jobs[i].finish_type = _frame_type_code(fin[1])
+            outs.append(out)
             if want_latents:
                 lat = torch.empty((d.n_symbols(),), dtype=torch.int8, device=self.torch_device)
                 lats.append(lat)

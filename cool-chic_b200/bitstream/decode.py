@@ -43,6 +43,17 @@ def _parse_frame(bitstream_bytes: bytes):
     return frame_header, ccs, rest
 
 
+def _finish_request(frame_header: FrameHeader, ccs):
+    """(bitdepth, frame_data_type) when the frame tail can be fused into the synthesis of this frame's Cool-chic:
+    an I frame whose Cool-chic has 3 output channels at the image size (else None: separate kernel)."""
+    if frame_header.get_value("frame_type") != "I":
+        return None
+    p = ccs["residue"][0].get_coolchic_parameter()
+    if int(p.layers_synthesis[-1].split("-")[0]) != 3 or p.latent_resolution[0] != 0:
+        return None
+    return (frame_header.get_value("bitdepth"), frame_header.get_value("frame_data_type"))
+
+
 def _reconstruct(frame_header: FrameHeader, cc_out: Dict[str, torch.Tensor], reference_frames: List[FrameData],
                  device: int) -> FrameData:
     """decode.py:155-212."""
@@ -52,9 +63,12 @@ def _reconstruct(frame_header: FrameHeader, cc_out: Dict[str, torch.Tensor], ref
     frame_data_type = frame_header.get_value("frame_data_type")
     if frame_type == "I":
         decoded = cc_out["residue"]
-        if decoded.size(1) != 3:
-            raise ValueError(f"Frame reconstruction expects 3 channels, found {decoded.size(1)}")
-        data = ctx.finish_frame(decoded, bitdepth, frame_data_type)
+        if cc_out.get("finished"):
+            data = decoded  # the synthesis kernel already applied the frame tail
+        else:
+            if decoded.size(1) != 3:
+                raise ValueError(f"Frame reconstruction expects 3 channels, found {decoded.size(1)}")
+            data = ctx.finish_frame(decoded, bitdepth, frame_data_type)
     else:
         # prediction + blending + residue + frame tail: one kernel, 4:2:0 references read in place
         refs = [r.to(ctx.torch_device) for r in reference_frames]
@@ -73,12 +87,15 @@ def decode_frame(bitstream_bytes: bytes, reference_frames: List[FrameData], verb
     if verbosity:
         print(frame_header.pretty_string())
     names = list(ccs)
+    fin = _finish_request(frame_header, ccs)
     outs = decode_coolchics([ccs[n][0] for n in names], [ccs[n][1] for n in names], [ccs[n][2] for n in names],
-                            device=device)
+                            device=device, finish=[fin if n == "residue" else None for n in names])
     if verbosity:
         for n in names:
             print(ccs[n][0].pretty_string())
-    frame = _reconstruct(frame_header, dict(zip(names, outs)), reference_frames, device)
+    cc_out = dict(zip(names, outs))
+    cc_out["finished"] = fin is not None
+    frame = _reconstruct(frame_header, cc_out, reference_frames, device)
     return frame, rest
 
 
@@ -105,8 +122,17 @@ def _decode_all_coolchics(parsed, device: int, decode_fn=None) -> List[Dict[str,
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     mine = shard_indices(len(flat), rank, world)
-    outs_mine = decode_fn([hdr[k] for k in mine], [parsed[flat[k][0]][1][flat[k][1]][1] for k in mine],
-                          [parsed[flat[k][0]][1][flat[k][1]][2] for k in mine], device=device)
+    fins = [None] * len(flat)
+    if world == 1 and decode_fn is decode_coolchics:
+        for k, (i, name) in enumerate(flat):
+            if name == "residue":
+                fins[k] = _finish_request(parsed[i][0], parsed[i][1])
+        outs_mine = decode_fn([hdr[k] for k in mine], [parsed[flat[k][0]][1][flat[k][1]][1] for k in mine],
+                              [parsed[flat[k][0]][1][flat[k][1]][2] for k in mine], device=device,
+                              finish=[fins[k] for k in mine])
+    else:
+        outs_mine = decode_fn([hdr[k] for k in mine], [parsed[flat[k][0]][1][flat[k][1]][1] for k in mine],
+                              [parsed[flat[k][0]][1][flat[k][1]][2] for k in mine], device=device)
     outs: List[Optional[torch.Tensor]] = [None] * len(flat)
     for k, o in zip(mine, outs_mine):
         outs[k] = o
@@ -119,8 +145,10 @@ def _decode_all_coolchics(parsed, device: int, decode_fn=None) -> List[Dict[str,
                 outs[k] = torch.empty(output_shape(hdr[k]), dtype=torch.float32, device=dev)
             dist.broadcast(outs[k], src=owner)
     cc_out: List[Dict[str, torch.Tensor]] = [dict() for _ in parsed]
-    for (i, name), o in zip(flat, outs):
+    for k, ((i, name), o) in enumerate(zip(flat, outs)):
         cc_out[i][name] = o
+        if fins[k] is not None:
+            cc_out[i]["finished"] = True
     return cc_out
 
 
@@ -172,11 +200,64 @@ def decode_video_bytes(bitstream_bytes: bytes, decoded_path: Optional[str] = Non
         frame = coding_structure.get_frame_from_display_order(display_idx)
         if frame is None or frame.data is None:
             continue
-        data = frame.data if output_device == "cuda" else frame.data.to(output_device)
+        fd = frame.data
+        on_gpu = (fd.data["y"] if fd.frame_data_type == "yuv420" else fd.data).is_cuda
+        if on_gpu and output_device != "cuda":
+            # device -> host as PACKED integer samples (1 or 2 bytes each instead of 4): the writers take them as they
+            # are, the float container of the API is rebuilt on the host (k / (2^b - 1) in fp32: the same values)
+            data = _to_host_packed(fd, device, decoded_path, append=display_idx != 0)
+        else:
+            data = fd if output_device == "cuda" else fd.to(output_device)
+            if decoded_path is not None:
+                save_frame_data_to_file(data, decoded_path, append=display_idx != 0)
         all_frames[str(display_idx)] = data
-        if decoded_path is not None:
-            save_frame_data_to_file(data, decoded_path, append=display_idx != 0)
     return all_frames
+
+
+def _to_host_packed(fd: FrameData, device: int, decoded_path: Optional[str], append: bool) -> FrameData:
+    import os
+
+    import numpy as np
+
+    from ..io.io import POSSIBLE_EXT, write_packed_ppm, write_packed_png, write_packed_yuv
+
+    ctx = _native.get_context(device)
+    b, fmt = fd.bitdepth, fd.frame_data_type
+    planar = ctx.pack_frame(fd.data, b, fmt).cpu().numpy()
+    planar = planar.view(np.uint8 if b <= 8 else np.uint16)
+    M = float(2**b - 1)
+    if fmt == "yuv420":
+        h, w = fd.data["y"].shape[-2:]
+        n0, n1 = h * w, (h // 2) * (w // 2)
+        parts = {"y": planar[:n0].reshape(1, 1, h, w), "u": planar[n0:n0 + n1].reshape(1, 1, h // 2, w // 2),
+                 "v": planar[n0 + n1:].reshape(1, 1, h // 2, w // 2)}
+        data = {k: torch.from_numpy(v.astype(np.float32)) / M for k, v in parts.items()}
+    else:
+        h, w = fd.data.shape[-2:]
+        data = torch.from_numpy(planar.reshape(1, 3, h, w).astype(np.float32)) / M
+    host = FrameData(bitdepth=b, frame_data_type=fmt, data=data)
+    if decoded_path is not None:
+        ext = os.path.splitext(decoded_path)[1]
+        assert ext in POSSIBLE_EXT, (
+            f"The function save_frame_data_to_file() expects a file ending with {POSSIBLE_EXT}. Found {decoded_path}"
+        )
+        if ext == ".yuv":
+            write_packed_yuv(planar, b, fmt, decoded_path, append)
+        else:
+            assert fmt == "rgb", (
+                "The function save_frame_data_to_file() can only save a RGB data "
+                f"into a {ext[1:].upper()} file. Found frame_data_type = {fmt}."
+            )
+            hwc = ctx.pack_frame(fd.data, b, fmt, interleaved=True).cpu().numpy().view(np.uint8 if b <= 8 else np.uint16)
+            if ext == ".png":
+                assert b == 8, (
+                    "The function save_frame_data_to_file() can only write 8-bit data "
+                    f"into a PNG file. Found bitdepth = {b}."
+                )
+                write_packed_png(hwc.reshape(h, w, 3), decoded_path)
+            else:
+                write_packed_ppm(hwc.reshape(h, w, 3), b, decoded_path)
+    return host
 
 
 def decode_video(bitstream_path: str, decoded_path: Optional[str] = None, max_decoding_order: int = -1,

@@ -386,6 +386,13 @@ struct PreparedJob {
     size_t smem = 0;
     int64_t n_sym = 0;
     int64_t lat_off_by_grid[CCD_MAX_GRIDS];
+    bool pad_lat = false;   // latents owned by the library: every grid starts on a 16-byte boundary (TMA source)
+    int64_t lat_bytes = 0;  // bytes of the latent buffer in that layout
+    // batched float tail (run_tail_batched)
+    bool tail = false;      // goes through the batched path
+    int tail_nl = 0, tail_gl[CCD_MAX_GRIDS];
+    int tail_cinp = 0, tail_C = 0;
+    size_t off_tailP = 0, off_tailQ = 0, off_tailRaw = 0, off_rawtmp = 0;  // inside the synthesis scratch
     // device offsets inside the upload arena
     size_t off_words = 0, off_blob = 0, off_status = 0, off_syn = 0, off_lat = 0;
     std::vector<float> syn_f;  // dequantised synthesis weights, packed
@@ -471,12 +478,15 @@ int prepare_job(PreparedJob &P, const int64_t *nn_ints_opt) {
     }
     const int64_t *nn = P.nn.data();
     // ---- latent layout (decode order: coarsest first)
-    int64_t off = 0;
+    int64_t off = 0, nsym = 0;
     for (int g = d->n_grids - 1; g >= 0; g--) {
+        if (P.pad_lat) off = (off + 15) & ~(int64_t)15;
         P.lat_off_by_grid[g] = off;
         off += (int64_t)d->grid_h[g] * d->grid_w[g];
+        nsym += (int64_t)d->grid_h[g] * d->grid_w[g];
     }
-    P.n_sym = off;
+    P.n_sym = nsym;
+    P.lat_bytes = off;
     if (off >= ((int64_t)1 << 31)) return fail(CCD_ERR_UNSUPPORTED, "more than 2^31 latent symbols");
     // ---- ARM + IFCE integers
     const int dim = L.dim;
@@ -824,6 +834,62 @@ int run_synthesis(CcdContext *ctx, const PreparedJob &P, const int8_t *d_lat, co
 
 size_t synthesis_scratch_bytes(const CcdCoolChicDesc *d) { return syn_scratch_plan(d).total + 4096; }
 
+// ---- batched float tail ------------------------------------------------------------------------------------
+// A job takes the batched path when its upsampling uses the default kernel sizes (8 / 7), it has at least two
+// latent grids, no common randomness, and its synthesis is in the fused family.  All such jobs of a call share
+//   * one launch per cascade level (all but the last), and
+//   * one launch (per (cinp, C) pair) of the kernel that evaluates the last level, the synthesis and -- for I
+//     frames that ask for it -- the frame tail.
+bool tail_eligible(const CcdCoolChicDesc *d, const NNLayout &L, PreparedJob &P) {
+    if (d->ups_k != 8 || d->ups_pre_k != 7 || d->common_randomness) return false;
+    int nl = 0;
+    for (int g = 0; g < d->n_grids; g++)
+        if (!d->grid_is_hyper[g]) P.tail_gl[nl++] = g;
+    if (nl < 2 || nl > 16 || nl != d->syn_in) return false;
+    const int nlay = d->n_syn_layers;
+    if (nlay < 2 || nlay > 4) return false;
+    const int C = d->syn_out[1];
+    if (d->syn_k[0] != 1 || d->syn_k[1] != 1 || d->syn_res[0] || d->syn_res[1] || d->syn_out[0] > 256 || C < 2 || C > 5) return false;
+    if (L.syn_c != C) return false;
+    for (int l = 2; l < nlay; l++)
+        if (d->syn_k[l] != 3 || d->syn_out[l] != C) return false;
+    if (d->syn_stab && L.syn_stab_in > nl) return false;
+    for (int i = 0; i + 1 < nl; i++) {
+        const int gt = P.tail_gl[i], gc = P.tail_gl[i + 1];
+        if (d->grid_h[gt] > 2 * d->grid_h[gc] || d->grid_w[gt] > 2 * d->grid_w[gc]) return false;  // (reported by the generic path)
+    }
+    P.tail_nl = nl;
+    P.tail_cinp = nl <= 4 ? 4 : (nl <= 8 ? 8 : 16);
+    P.tail_C = C;
+    return true;
+}
+
+struct TailScratch {
+    size_t p = 0, q = 0, raw = 0, total = 0;
+};
+TailScratch tail_scratch_plan(const CcdCoolChicDesc *d, const PreparedJob &P) {
+    TailScratch T;
+    const int nl = P.tail_nl;
+    size_t o = 0;
+    if (nl >= 3) {
+        const int g1 = P.tail_gl[1];
+        T.p = o;
+        o += al((size_t)(nl - 1) * d->grid_h[g1] * d->grid_w[g1] * 4);
+    }
+    if (nl >= 4) {
+        const int g2 = P.tail_gl[2];
+        T.q = o;
+        o += al((size_t)(nl - 2) * d->grid_h[g2] * d->grid_w[g2] * 4);
+    }
+    const int g0 = P.tail_gl[0];
+    if (d->grid_h[g0] != d->img_h || d->grid_w[g0] != d->img_w) {
+        T.raw = o;
+        o += al((size_t)P.tail_C * d->grid_h[g0] * d->grid_w[g0] * 4);
+    }
+    T.total = o;
+    return T;
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -951,11 +1017,14 @@ static int decode_impl_body(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
     std::vector<PreparedJob> P((size_t)n_jobs);
-    size_t up = 0, scratch_syn = 0, scratch_lat = 0;
+    size_t up = 0, scratch_syn = 0, scratch_lat = 0, scratch_tail = 0;
+    size_t n_tail = 0, n_tail_levels = 0;
     for (int i = 0; i < n_jobs; i++) {
         P[(size_t)i].job = &jobs[i];
         P[(size_t)i].d = jobs[i].desc;
         jobs[i].status = CCD_OK;
+        const bool own_lat = !(jobs[i].d_latents || (d_lat_in && d_lat_in[i]));
+        P[(size_t)i].pad_lat = own_lat && mode == 0;
         int rc = prepare_job(P[(size_t)i], nn_ints ? nn_ints[i] : nullptr);
         if (rc) {
             jobs[i].status = rc;
@@ -973,19 +1042,49 @@ static int decode_impl_body(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int
         up += al(64);
         J.off_syn = up;
         up += al(J.syn_f.size() * 4);
-        if (stages & 2) scratch_syn = std::max(scratch_syn, synthesis_scratch_bytes(J.d));
-        const bool own_lat = !(jobs[i].d_latents || (d_lat_in && d_lat_in[i]));
+        if (stages & 2) {
+            if (jobs[i].finish_bitdepth != 0) {
+                if (jobs[i].finish_bitdepth < 1 || jobs[i].finish_bitdepth > 16 || jobs[i].finish_type < 0 || jobs[i].finish_type > 3)
+                    return fail(CCD_ERR_ARG, "job %d: bad frame tail request (bitdepth %d, type %d)", i, jobs[i].finish_bitdepth, jobs[i].finish_type);
+                if (J.L.syn_c != 3) return fail(CCD_ERR_ARG, "job %d: the frame tail needs a 3-channel output, found %d", i, J.L.syn_c);
+                if (jobs[i].finish_type == 1 && (!jobs[i].d_out_u || !jobs[i].d_out_v))
+                    return fail(CCD_ERR_ARG, "job %d: yuv420 frame tail needs u and v outputs", i);
+            }
+            J.tail = ctx->fused_synthesis && tail_eligible(J.d, J.L, J);
+            if (J.tail) {
+                const TailScratch T = tail_scratch_plan(J.d, J);
+                J.off_tailP = scratch_tail + T.p;
+                J.off_tailQ = scratch_tail + T.q;
+                J.off_tailRaw = scratch_tail + T.raw;
+                scratch_tail += al(T.total);
+                n_tail++;
+                n_tail_levels += (size_t)(J.tail_nl - 2);
+            } else {
+                size_t need = synthesis_scratch_bytes(J.d);
+                if (jobs[i].finish_bitdepth != 0) {  // raw output first, then the frame tail kernel
+                    J.off_rawtmp = al(need);
+                    need = J.off_rawtmp + al((size_t)3 * J.d->img_h * J.d->img_w * 4);
+                }
+                scratch_syn = std::max(scratch_syn, need);
+            }
+        }
         J.off_lat = scratch_lat;
-        if (own_lat) scratch_lat += al((size_t)J.n_sym);
+        if (own_lat) scratch_lat += al((size_t)J.lat_bytes);
     }
+    // device-resident job arrays of the batched float tail (filled below, uploaded with everything else)
+    const size_t off_tail_syn = up;
+    up += al(n_tail * ccd_tail_job_bytes());
+    const size_t off_tail_lvl = up;
+    up += al(n_tail_levels * ccd_tail_level_job_bytes());
     const size_t off_streams = up;
     up += al(sizeof(EntStream) * (size_t)n_jobs);
     int rc;
     if ((rc = ensure_pin(ctx, up))) return rc;
     if ((rc = ensure_dev(ctx->upload, up))) return rc;
-    if ((rc = ensure_dev(ctx->scratch, scratch_lat + scratch_syn + 4096))) return rc;
+    if ((rc = ensure_dev(ctx->scratch, scratch_lat + al(scratch_syn) + scratch_tail + 4096))) return rc;
     unsigned char *h = ctx->h_pin, *dv = ctx->upload.p;
     unsigned char *d_scr_syn = ctx->scratch.p + scratch_lat;
+    unsigned char *d_scr_tail = d_scr_syn + al(scratch_syn);
 
     // group jobs by kernel configuration so that each group is one launch
     std::vector<int> order((size_t)n_jobs);
@@ -1023,6 +1122,118 @@ static int decode_impl_body(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int
     }
     for (int t = 0; t < n_jobs; t++)
         memcpy(h + off_streams + sizeof(EntStream) * (size_t)t, &P[(size_t)order[(size_t)t]].es, sizeof(EntStream));
+
+    // ---- batched float tail: job arrays.  Launch groups: cascade level `idx` of every stream that has one
+    // (planes = idx + 2), then one launch per (cinp, C) pair for the last level + synthesis (+ frame tail).
+    struct TailGroup { int cinp, C, n3_max, hid_max, max_w, max_h, first, count; };
+    std::vector<TailGroup> tail_groups;
+    struct TailLevelLaunch { size_t first; int count, planes, max_tw, max_th; };
+    std::vector<TailLevelLaunch> tail_levels;
+    std::vector<int> tail_order;  // jobs of the batched path, sorted by (cinp, C)
+    if (n_tail) {
+        for (int i = 0; i < n_jobs; i++)
+            if (P[(size_t)i].tail) tail_order.push_back(i);
+        std::stable_sort(tail_order.begin(), tail_order.end(), [&](int a, int b) {
+            const PreparedJob &A = P[(size_t)a], &B = P[(size_t)b];
+            return A.tail_cinp * 8 + A.tail_C < B.tail_cinp * 8 + B.tail_C;
+        });
+        const size_t jb = ccd_tail_job_bytes(), lb = ccd_tail_level_job_bytes();
+        // cascade levels
+        int max_levels = 0;
+        for (int i : tail_order) max_levels = std::max(max_levels, P[(size_t)i].tail_nl - 2);
+        size_t lvl_at = 0;
+        for (int idx = 0; idx < max_levels; idx++) {
+            TailLevelLaunch LL{lvl_at, 0, idx + 2, 0, 0};
+            for (int i : tail_order) {
+                const PreparedJob &J = P[(size_t)i];
+                const CcdCoolChicDesc *d = J.d;
+                const int nl = J.tail_nl;
+                if (idx >= nl - 2) continue;
+                const int gt = J.tail_gl[nl - 2 - idx], gc = J.tail_gl[nl - 1 - idx];
+                float par_t[8], par_c[8], full_t[16], full_c[16];
+                const float qs_uw = ldexpf(1.0f, d->qshift[4]);
+                const int kid = idx % d->n_ups;
+                for (int t = 0; t < J.L.kt_par; t++) par_t[t] = (float)J.nn[(size_t)(J.L.ups_tw + (int64_t)kid * J.L.kt_par + t)] * qs_uw;
+                for (int t = 0; t < J.L.kc_par; t++) par_c[t] = (float)J.nn[(size_t)(J.L.ups_cw + (int64_t)kid * J.L.kc_par + t)] * qs_uw;
+                expand_sym(par_t, d->ups_k, full_t);
+                expand_sym(par_c, d->ups_pre_k, full_c);
+                // level idx writes P when (nl - 3 - idx) is even (the last one, idx = nl - 3, always writes P)
+                const bool to_p = ((nl - 3 - idx) & 1) == 0;
+                float *out = reinterpret_cast<float *>(d_scr_tail + (to_p ? J.off_tailP : J.off_tailQ));
+                const float *in = reinterpret_cast<const float *>(d_scr_tail + (to_p ? J.off_tailQ : J.off_tailP));
+                const int8_t *in8 = idx == 0 ? d_lat[(size_t)i] + J.lat_off_by_grid[gc] : nullptr;
+                ccd_tail_fill_level(h + off_tail_lvl + (lvl_at + (size_t)LL.count) * lb, d_lat[(size_t)i] + J.lat_off_by_grid[gt],
+                                    idx == 0 ? nullptr : in, in8, out, idx + 1, d->grid_h[gc], d->grid_w[gc], d->grid_h[gt],
+                                    d->grid_w[gt], full_t, full_c);
+                LL.count++;
+                LL.max_tw = std::max(LL.max_tw, d->grid_w[gt]);
+                LL.max_th = std::max(LL.max_th, d->grid_h[gt]);
+            }
+            lvl_at += (size_t)LL.count;
+            if (LL.count) tail_levels.push_back(LL);
+        }
+        // last level + synthesis
+        const float *d_synw_base = reinterpret_cast<const float *>(dv);
+        for (size_t t = 0; t < tail_order.size(); t++) {
+            const int i = tail_order[t];
+            PreparedJob &J = P[(size_t)i];
+            const CcdCoolChicDesc *d = J.d;
+            const NNLayout &L = J.L;
+            const int nl = J.tail_nl, g0 = J.tail_gl[0], g1 = J.tail_gl[1];
+            const float *d_synw = reinterpret_cast<const float *>(dv + J.off_syn);
+            (void)d_synw_base;
+            SynLayerDev all[CCD_MAX_SYN];
+            int in_ft = d->syn_in;
+            for (int l = 0; l < d->n_syn_layers; l++) {
+                all[l] = SynLayerDev{in_ft, d->syn_out[l], d->syn_k[l], d->syn_res[l], d->syn_relu[l], d_synw + J.syn_off_w[l],
+                                     d_synw + J.syn_off_b[l]};
+                in_ft = d->syn_out[l];
+            }
+            const int C = J.tail_C;
+            SynLayerDev Ls{L.syn_stab_in, C, 1, 0, 0, d_synw + J.syn_off_st_w, d_synw + J.syn_off_st_b};
+            CcdTailSynDesc T;
+            memset(&T, 0, sizeof(T));
+            T.lat = d_lat[(size_t)i] + J.lat_off_by_grid[g0];
+            if (nl == 2) T.stk8 = d_lat[(size_t)i] + J.lat_off_by_grid[g1];
+            else T.stk = reinterpret_cast<const float *>(d_scr_tail + J.off_tailP);
+            T.h = d->grid_h[g0]; T.w = d->grid_w[g0]; T.ch = d->grid_h[g1]; T.cw = d->grid_w[g1]; T.cin = nl;
+            T.layers = all; T.n_layers = d->n_syn_layers; T.stab = d->syn_stab ? &Ls : nullptr;
+            T.ot = SynLayerDev{C, C, 1, 0, 0, d_synw + J.syn_off_ot_w, d_synw + J.syn_off_ot_b};
+            const bool same = (T.h == d->img_h && T.w == d->img_w);
+            const size_t plane = (size_t)T.h * T.w;
+            const CcdJob &job = jobs[i];
+            if (!same) {
+                float *raw = reinterpret_cast<float *>(d_scr_tail + J.off_tailRaw);
+                for (int c = 0; c < C; c++) T.out[c] = raw + (size_t)c * plane;
+            } else if (job.finish_bitdepth != 0 && job.finish_type == 1) {
+                T.out[0] = job.d_out; T.out[1] = job.d_out_u; T.out[2] = job.d_out_v;
+                T.finish = 2;
+            } else {
+                for (int c = 0; c < C; c++) T.out[c] = job.d_out + (size_t)c * plane;
+                T.finish = job.finish_bitdepth != 0 ? 1 : 0;
+            }
+            T.M = job.finish_bitdepth != 0 ? (float)((1 << job.finish_bitdepth) - 1) : 0.0f;
+            float par_t[8], par_c[8], full_t[16], full_c[16];
+            const float qs_uw = ldexpf(1.0f, d->qshift[4]);
+            const int kid = (nl - 2) % d->n_ups;
+            for (int k = 0; k < L.kt_par; k++) par_t[k] = (float)J.nn[(size_t)(L.ups_tw + (int64_t)kid * L.kt_par + k)] * qs_uw;
+            for (int k = 0; k < L.kc_par; k++) par_c[k] = (float)J.nn[(size_t)(L.ups_cw + (int64_t)kid * L.kc_par + k)] * qs_uw;
+            expand_sym(par_t, d->ups_k, full_t);
+            expand_sym(par_c, d->ups_pre_k, full_c);
+            T.wt1d = full_t; T.wc1d = full_c;
+            T.allow_tma = J.pad_lat ? 1 : 0;
+            const int tr = ccd_tail_fill_syn(h + off_tail_syn + t * jb, T);
+            if (tr < 0) return fail(CCD_ERR_ARG, "internal: job %d is not in the fused synthesis family", i);
+            if (tail_groups.empty() || tail_groups.back().cinp != J.tail_cinp || tail_groups.back().C != C)
+                tail_groups.push_back(TailGroup{J.tail_cinp, C, 0, 0, 0, 0, (int)t, 0});
+            TailGroup &G = tail_groups.back();
+            G.count++;
+            G.n3_max = std::max(G.n3_max, d->n_syn_layers - 2);
+            G.hid_max = std::max(G.hid_max, d->syn_out[0]);
+            G.max_w = std::max(G.max_w, T.w);
+            G.max_h = std::max(G.max_h, T.h);
+        }
+    }
     CUDA_TRY(cudaMemcpyAsync(dv, h, up, cudaMemcpyHostToDevice, st));
     ctx->last_upload_bytes = up;
     CUDA_TRY(cudaEventRecord(ctx->ev[1], st));
@@ -1063,12 +1274,50 @@ static int decode_impl_body(CcdContext *ctx, CcdJob *jobs, int n_jobs, const int
     }
     CUDA_TRY(cudaEventRecord(ctx->ev[2], st));
     if (stages & 2) {
+        // batched path: all cascade levels, then the fused last level + synthesis (+ frame tail)
+        const size_t jb = ccd_tail_job_bytes(), lb = ccd_tail_level_job_bytes();
+        for (const TailLevelLaunch &LL : tail_levels)
+            if (ccd_tail_launch_level(dv + off_tail_lvl + LL.first * lb, LL.count, LL.planes, LL.max_tw, LL.max_th, st))
+                return fail(CCD_ERR_CUDA, "cascade level launch failed");
+        for (const TailGroup &G : tail_groups) {
+            const int e = ccd_tail_launch_syn(dv + off_tail_syn + (size_t)G.first * jb, G.count, G.cinp, G.C, G.n3_max, G.hid_max,
+                                              G.max_w, G.max_h, st);
+            if (e != 0) return fail(CCD_ERR_CUDA, "fused tail launch failed (%d)", e);
+        }
+        for (int i : tail_order) {
+            // grids smaller than the image (motion fields): final F.interpolate (component/coolchic.py:187-192)
+            const PreparedJob &J = P[(size_t)i];
+            const CcdCoolChicDesc *d = J.d;
+            const int g0 = J.tail_gl[0], h0 = d->grid_h[g0], w0 = d->grid_w[g0];
+            if (h0 == d->img_h && w0 == d->img_w) continue;
+            const float *raw = reinterpret_cast<const float *>(d_scr_tail + J.off_tailRaw);
+            float *dst = jobs[i].d_out;
+            unsigned char *tmp = nullptr;
+            if (jobs[i].finish_bitdepth != 0) return fail(CCD_ERR_UNSUPPORTED, "job %d: frame tail on a resized output", i);
+            (void)tmp;
+            if (d->final_ups == 0)
+                rc = ccd_resize_nearest(raw, J.tail_C, h0, w0, dst, d->img_h, d->img_w, st);
+            else
+                rc = ccd_resize_torch(raw, J.tail_C, h0, w0, dst, d->img_h, d->img_w, d->final_ups == 1 ? 1 : 2,
+                                      (float)h0 / (float)d->img_h, (float)w0 / (float)d->img_w, st);
+            if (rc) return fail(CCD_ERR_CUDA, "resize launch");
+        }
+        // everything else: one stream after the other through the general kernels
         for (int i = 0; i < n_jobs; i++) {
+            if (P[(size_t)i].tail) continue;
+            const bool fin = jobs[i].finish_bitdepth != 0;
+            float *raw_dst = fin ? reinterpret_cast<float *>(d_scr_syn + P[(size_t)i].off_rawtmp) : jobs[i].d_out;
             rc = run_synthesis(ctx, P[(size_t)i], d_lat[(size_t)i], reinterpret_cast<const float *>(dv + P[(size_t)i].off_syn),
-                               jobs[i].d_out, d_scr_syn, scratch_syn, st);
+                               raw_dst, d_scr_syn, scratch_syn, st);
             if (rc) {
                 jobs[i].status = rc;
                 return rc;
+            }
+            if (fin) {
+                const int ft = jobs[i].finish_type == 3 ? 2 : jobs[i].finish_type;
+                if (ccd_finish(raw_dst, P[(size_t)i].d->img_h, P[(size_t)i].d->img_w, jobs[i].finish_bitdepth, ft, jobs[i].d_out,
+                               jobs[i].d_out_u, jobs[i].d_out_v, st))
+                    return fail(CCD_ERR_CUDA, "finish_frame launch failed");
             }
         }
     }
@@ -1101,14 +1350,14 @@ int ccd_decode_many(CcdContext *ctx, CcdJob *jobs, int n_jobs, void *cuda_stream
 int ccd_decode_coolchic(CcdContext *ctx, const CcdCoolChicDesc *desc, const uint8_t *nn_bytes, size_t nn_nbytes,
                         const uint8_t *latent_bytes, size_t latent_nbytes, float *d_out, int8_t *d_latents,
                         void *cuda_stream) {
-    CcdJob j{desc, nn_bytes, nn_nbytes, latent_bytes, latent_nbytes, d_out, d_latents, 0};
+    CcdJob j{desc, nn_bytes, nn_nbytes, latent_bytes, latent_nbytes, d_out, d_latents, 0, 0, 0, nullptr, nullptr};
     return ccd_decode_many(ctx, &j, 1, cuda_stream);
 }
 
 int ccd_decode_latents(CcdContext *ctx, const CcdCoolChicDesc *desc, const int64_t *nn_ints, const uint8_t *latent_bytes,
                        size_t latent_nbytes, int8_t *d_latents, void *cuda_stream) {
     if (!d_latents || !nn_ints) return fail(CCD_ERR_ARG, "null pointer");
-    CcdJob j{desc, nullptr, 0, latent_bytes, latent_nbytes, nullptr, d_latents, 0};
+    CcdJob j{desc, nullptr, 0, latent_bytes, latent_nbytes, nullptr, d_latents, 0, 0, 0, nullptr, nullptr};
     const int64_t *nn[1] = {nn_ints};
     return decode_impl(ctx, &j, 1, nn, 1, nullptr, 0, 0, nullptr, 0, nullptr, cuda_stream);
 }
@@ -1116,7 +1365,7 @@ int ccd_decode_latents(CcdContext *ctx, const CcdCoolChicDesc *desc, const int64
 int ccd_synthesize(CcdContext *ctx, const CcdCoolChicDesc *desc, const int64_t *nn_ints, const int8_t *d_latents,
                    float *d_out, void *cuda_stream) {
     if (!d_latents || !nn_ints || !d_out) return fail(CCD_ERR_ARG, "null pointer");
-    CcdJob j{desc, nullptr, 0, nullptr, 0, d_out, nullptr, 0};
+    CcdJob j{desc, nullptr, 0, nullptr, 0, d_out, nullptr, 0, 0, 0, nullptr, nullptr};
     const int64_t *nn[1] = {nn_ints};
     const int8_t *lat[1] = {d_latents};
     return decode_impl(ctx, &j, 1, nn, 2, lat, 0, 0, nullptr, 0, nullptr, cuda_stream);
@@ -1126,7 +1375,7 @@ int ccd_encode_latents(CcdContext *ctx, const CcdCoolChicDesc *desc, const int64
                        int8_t *d_latents, uint32_t *d_out_words, int64_t out_cap_words, int64_t *n_words_out,
                        int32_t *slow_out, void *cuda_stream) {
     if (!d_latents || !nn_ints || !d_out_words || (mode != 1 && mode != 2)) return fail(CCD_ERR_ARG, "bad argument");
-    CcdJob j{desc, nullptr, 0, nullptr, 0, nullptr, d_latents, 0};
+    CcdJob j{desc, nullptr, 0, nullptr, 0, nullptr, d_latents, 0, 0, 0, nullptr, nullptr};
     const int64_t *nn[1] = {nn_ints};
     uint32_t *ow[1] = {d_out_words};
     int32_t stt[1][16];

@@ -113,6 +113,32 @@ int ccd_syn_pointwise2(const float *d_in, int h, int w, const SynLayerDev &L0, c
 int ccd_syn_fused(const float *d_in, int h, int w, int cin, const SynLayerDev *layers, int n_layers,
                   const SynLayerDev *stab, const SynLayerDev &ot, float *d_out, cudaStream_t st);
 int ccd_syn_add(float *d_a, const float *d_b, size_t n, cudaStream_t st);
+
+// ---- batched float tail (ccd_synth.cu): device-resident job arrays, one launch per cascade level and one for
+// the last level + synthesis + frame tail of ALL streams of a group
+struct CcdTailSynDesc {
+    const int8_t *lat;        // finest latent grid [h][w]
+    const float *stk;         // coarser stack [cin - 1][ch][cw] (fp32), or ...
+    const int8_t *stk8;       // ... the coarsest latent itself when the stream has two grids
+    float *out[5];            // output planes
+    int h, w, ch, cw, cin;
+    const SynLayerDev *layers;
+    int n_layers;
+    const SynLayerDev *stab;  // may be null
+    SynLayerDev ot;
+    int finish;               // 0 raw, 1 frame tail (full planes), 2 frame tail 4:2:0
+    float M;
+    const float *wt1d, *wc1d; // 8 / 7 taps of the last cascade level
+    int allow_tma;
+};
+size_t ccd_tail_job_bytes(void);
+size_t ccd_tail_level_job_bytes(void);
+void ccd_tail_fill_level(void *dst, const int8_t *lat, const float *in, const int8_t *in8, float *out, int cc, int ch,
+                         int cw, int th, int tw, const float *wt1d, const float *wc1d);
+int ccd_tail_launch_level(const void *d_jobs, int n_jobs, int planes, int max_tw, int max_th, cudaStream_t st);
+int ccd_tail_fill_syn(void *dst, const CcdTailSynDesc &T);
+int ccd_tail_launch_syn(const void *d_jobs, int n_jobs, int cinp, int C, int n3_max, int hid_max, int max_w, int max_h,
+                        cudaStream_t st);
 int ccd_resize_nearest(const float *d_in, int c, int h, int w, float *d_out, int H, int W, cudaStream_t st);
 // F.interpolate bilinear (mode 1) / bicubic (mode 2), align_corners=False; sy/sx = 0.5 (scale_factor 2) or in/out
 int ccd_resize_torch(const float *d_in, int c, int h, int w, float *d_out, int H, int W, int mode, float sy, float sx,

@@ -14,6 +14,7 @@
 // every output is acc = init; for ci, for ky, for kx: acc = fmaf(w, x, acc).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "ccd_detmath.h"
 #include "ccd_internal.h"
@@ -429,6 +430,455 @@ __global__ void __launch_bounds__(SF_THREADS) k_syn_fused(SynFusedParams P) {
     }
 }
 
+// ===================================================================================================
+// Batched float tail (BASELINE configs[2] / [4]: many streams in one call).
+//
+//   k_ups_level_b : one level of the cascade for ALL streams of a group in one launch
+//                   (blockIdx.z = stream * planes + plane)
+//   k_tail_syn    : the LAST cascade level + the whole synthesis + the frame tail in one kernel.  The dense
+//                   latent at image resolution (7 fp32 planes, 28 B / pixel written and read back by the
+//                   unfused path) is never materialised: a CTA stages the int8 tile of the finest grid
+//                   (zero padding = TMA out-of-bounds fill) and the tile of the half-resolution stack in shared
+//                   memory -- with TMA (cp.async.bulk.tensor + mbarrier) when the row pitches allow it -- and
+//                   evaluates the 7x7 pre-concatenation conv and the 8x8 stride-2 transposed conv on the fly
+//                   for every position of the synthesis region.  Epilogue: output transform, then optionally
+//                   decode_frame's round / (4:2:0 average) / clamp / round (bitstream/decode.py:191-206).
+// Every output keeps the canonical fp32 operation order of the unfused kernels (bit-identical, tested).
+// ===================================================================================================
+struct UpsLevelJob {
+    const int8_t *lat;  // target grid [th][tw]
+    const float *in;    // coarser stack [cc][ch][cw] (fp32) ...
+    const int8_t *in8;  // ... or, for the first level, the coarsest latent grid itself (cc == 1)
+    float *out;         // [cc + 1][th][tw]
+    int cc, ch, cw, th, tw;
+    float kt[8][8];     // transposed-conv taps
+    float kc[7][7];     // pre-concatenation taps
+};
+__global__ void __launch_bounds__(256) k_ups_level_b(const UpsLevelJob *__restrict__ jobs, int planes) {
+    const int job = blockIdx.z / planes, plane = blockIdx.z - job * planes;
+    const UpsLevelJob &P = jobs[job];
+    if (plane > P.cc) return;
+    const int th = P.th, tw = P.tw;
+    if (plane == 0) {
+        const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+        if (x >= tw || y >= th) return;
+        float acc = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 7; a++) {
+            const int yy = y + a - 3;
+#pragma unroll
+            for (int b = 0; b < 7; b++) {
+                const int xx = x + b - 3;
+                if (yy >= 0 && yy < th && xx >= 0 && xx < tw) acc = __fmaf_rn(P.kc[a][b], (float)P.lat[(size_t)yy * tw + xx], acc);
+            }
+        }
+        P.out[(size_t)y * tw + x] = __fadd_rn(acc, (float)P.lat[(size_t)y * tw + x]);
+        return;
+    }
+    const int s0 = blockIdx.x * 32 + threadIdx.x, q = blockIdx.y * 8 + threadIdx.y;
+    if (2 * s0 >= tw || 2 * q >= th) return;
+    const int c = plane - 1, h = P.ch, w = P.cw;
+    float win[5][5];
+    if (P.in8) {
+        const int8_t *src = P.in8 + (size_t)c * h * w;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const int8_t *row = src + (size_t)clampi(q - 2 + i, 0, h - 1) * w;
+#pragma unroll
+            for (int j = 0; j < 5; j++) win[i][j] = (float)row[clampi(s0 - 2 + j, 0, w - 1)];
+        }
+    } else {
+        const float *src = P.in + (size_t)c * h * w;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            const float *row = src + (size_t)clampi(q - 2 + i, 0, h - 1) * w;
+#pragma unroll
+            for (int j = 0; j < 5; j++) win[i][j] = __ldg(row + clampi(s0 - 2 + j, 0, w - 1));
+        }
+    }
+    float *dst = P.out + (size_t)(c + 1) * th * tw;
+#pragma unroll
+    for (int du = 0; du < 2; du++) {
+        const int u = 2 * q + du;
+        if (u >= th) continue;
+#pragma unroll
+        for (int dv = 0; dv < 2; dv++) {
+            const int v = 2 * s0 + dv;
+            if (v >= tw) continue;
+            float acc = 0.0f;
+#pragma unroll
+            for (int t1 = 0; t1 < 4; t1++)
+#pragma unroll
+                for (int t2 = 0; t2 < 4; t2++)
+                    acc = __fmaf_rn(P.kt[(1 - du) + 6 - 2 * t1][(1 - dv) + 6 - 2 * t2], win[t1 + du][t2 + dv], acc);
+            dst[(size_t)u * tw + v] = acc;
+        }
+    }
+}
+
+struct alignas(64) TailSynJob {
+    unsigned char tmap_lat[128];  // CUtensorMap: finest latent grid, uint8 [h][w], box LW x LH
+    unsigned char tmap_stk[128];  // CUtensorMap: coarser stack, fp32 [cc][ch][cw], box SW x SH x cc
+    const int8_t *lat;            // finest grid [h][w]
+    const float *stk;             // coarser stack [cc][ch][cw] (cc = cin - 1), already upsampled to (ch, cw)
+    const int8_t *stk8;           // ... or the coarsest latent itself when only two grids exist (cc == 1)
+    float *out[3 + 2];            // output planes (C <= 5)
+    int h, w, ch, cw, cin, hid, n3;
+    int relu0, relu1, res3[2], relu3[2];
+    int stab_in;
+    int use_tma;
+    int finish;                   // 0: raw synthesis output; 1: frame tail, three full planes; 2: frame tail 4:2:0
+    float M;                      // 2^bitdepth - 1
+    const float *w0, *b0, *w1, *b1;
+    const float *w3[2], *b3[2];
+    const float *ws, *bs, *wo, *bo;
+    float kt[8][8], kc[7][7];
+};
+constexpr int TS_LW_MAX = 48, TS_LH_MAX = SF_TH + 4 + 6;              // int8 latent tile (n3 <= 2)
+constexpr int TS_SW_MAX = 24, TS_SH_MAX = (SF_TH + 4) / 2 + 5;        // half-resolution stack tile
+__host__ __device__ inline int ts_lw(int n3) { return (SF_TW + 2 * n3 + 6 + 15) & ~15; }
+__host__ __device__ inline int ts_lh(int n3) { return SF_TH + 2 * n3 + 6; }
+__host__ __device__ inline int ts_sw(int n3) { return ((SF_TW + 2 * n3) / 2 + 5 + 3) & ~3; }
+__host__ __device__ inline int ts_sh(int n3) { return (SF_TH + 2 * n3) / 2 + 5; }
+
+__device__ __forceinline__ float quant(float v, float M);
+__device__ __forceinline__ float clamp01(float v);
+
+template <int CINP, int C>
+__global__ void __launch_bounds__(SF_THREADS) k_tail_syn(const TailSynJob *__restrict__ jobs) {
+    extern __shared__ __align__(128) unsigned char ts_raw[];
+    const TailSynJob &P = jobs[blockIdx.z];
+    const int H = P.h, W = P.w;
+    const int x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
+    if (x0 >= W || y0 >= H) return;  // (streams of one launch may have different sizes)
+    const int n3 = P.n3, hid = P.hid, cin = P.cin, cc = cin - 1;
+    const int RW = SF_TW + 2 * n3, RH = SF_TH + 2 * n3;  // stage-A region
+    const int LW = ts_lw(n3), LH = ts_lh(n3), SW = ts_sw(n3), SH = ts_sh(n3);
+    constexpr int CP = (C + 3) & ~3;
+    // shared memory: [mbarrier 16 B] [latent tile] [stack tile] | weights, region buffers (floats)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ts_raw);
+    int8_t *Lt = reinterpret_cast<int8_t *>(ts_raw + 128);                          // [LH][LW]
+    float *St = reinterpret_cast<float *>(ts_raw + 128 + ((LW * LH + 127) & ~127)); // [cc][SH][SW]
+    float *sw0 = St + ((cc * SH * SW + 31) & ~31);  // [hid][CINP]
+    float *sb0 = sw0 + hid * CINP;
+    float *sw1 = sb0 + hid;                  // [hid][CP]
+    float *sb1 = sw1 + hid * CP;
+    float *sw3 = sb1 + CP;                   // [2][C][C][9]
+    float *sb3 = sw3 + 2 * C * C * 9;
+    float *sws = sb3 + 2 * CP;               // [C][CINP]
+    float *sbs = sws + C * CINP;
+    float *swo = sbs + CP;                   // [C][CP]
+    float *sbo = swo + C * CP;
+    float *skt = sbo + CP;                   // [8][8]
+    float *skc = skt + 64;                   // [7][7] (+ pad)
+    float *bufA = skc + 52;                  // [C][RH][RW]
+    float *bufB = bufA + C * RH * RW;        // [C][RH-2][RW-2]   (n3 == 2)
+    float *sstab = bufB + (n3 == 2 ? C * (RH - 2) * (RW - 2) : 0);  // [C][SF_TH][SF_TW]
+    const int tid = threadIdx.x;
+    // tile origins (frame coordinates of element 0 of the tiles)
+    const int Y0 = y0 - n3, X0 = x0 - n3;                   // stage-A region
+    const int ly0 = Y0 - 3, lx0 = X0 - 3;                   // latent tile
+    const int sy0 = ((Y0 < 0 ? 0 : Y0) >> 1) - 2, sx0 = ((X0 < 0 ? 0 : X0) >> 1) - 2;  // stack tile
+    const int ch = P.ch, cw = P.cw;
+    // ---- stage 0: tiles -> shared memory
+    if (P.use_tma) {
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(LW * LH + cc * SH * SW * 4);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            const uint64_t tm0 = reinterpret_cast<uint64_t>(P.tmap_lat), tm1 = reinterpret_cast<uint64_t>(P.tmap_stk);
+            // the descriptors live in global memory (one pair per stream of the launch, written by the host)
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm0) : "memory");
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm1) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"((uint32_t)__cvta_generic_to_shared(Lt)), "l"(tm0), "r"(lx0), "r"(ly0), "r"(bar_a)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"((uint32_t)__cvta_generic_to_shared(St)), "l"(tm1), "r"(sx0), "r"(sy0), "r"(0), "r"(bar_a)
+                : "memory");
+        }
+    } else {
+        for (int i = tid; i < LW * LH; i += SF_THREADS) {
+            const int r = i / LW, c = i - r * LW;
+            const int gy = ly0 + r, gx = lx0 + c;
+            Lt[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? P.lat[(size_t)gy * W + gx] : (int8_t)0;
+        }
+        for (int i = tid; i < cc * SH * SW; i += SF_THREADS) {
+            const int c = i / (SH * SW), rem = i - c * SH * SW, r = rem / SW, col = rem - r * SW;
+            const int gy = sy0 + r, gx = sx0 + col;
+            float v = 0.0f;
+            if (gy >= 0 && gy < ch && gx >= 0 && gx < cw)
+                v = P.stk8 ? (float)P.stk8[((size_t)c * ch + gy) * cw + gx] : __ldg(P.stk + ((size_t)c * ch + gy) * cw + gx);
+            St[i] = v;
+        }
+    }
+    // ---- weights (overlaps the bulk copies)
+    for (int i = tid; i < hid * CINP; i += SF_THREADS) {
+        const int hh = i / CINP, ci = i - hh * CINP;
+        sw0[i] = ci < cin ? P.w0[hh * cin + ci] : 0.0f;
+    }
+    for (int i = tid; i < hid; i += SF_THREADS) sb0[i] = P.b0[i];
+    for (int i = tid; i < hid * CP; i += SF_THREADS) {
+        const int hh = i / CP, c = i - hh * CP;
+        sw1[i] = c < C ? P.w1[c * hid + hh] : 0.0f;
+    }
+    for (int i = tid; i < CP; i += SF_THREADS) {
+        sb1[i] = i < C ? P.b1[i] : 0.0f;
+        sbs[i] = (i < C && P.stab_in) ? P.bs[i] : 0.0f;
+        sbo[i] = i < C ? P.bo[i] : 0.0f;
+        for (int l = 0; l < 2; l++) sb3[l * CP + i] = (i < C && l < n3) ? P.b3[l][i] : 0.0f;
+    }
+    for (int l = 0; l < n3; l++)
+        for (int i = tid; i < C * C * 9; i += SF_THREADS) sw3[l * C * C * 9 + i] = P.w3[l][i];
+    for (int i = tid; i < C * CINP; i += SF_THREADS) {
+        const int c = i / CINP, ci = i - c * CINP;
+        sws[i] = (ci < P.stab_in) ? P.ws[c * P.stab_in + ci] : 0.0f;
+    }
+    for (int i = tid; i < C * CP; i += SF_THREADS) {
+        const int c = i / CP, k = i - c * CP;
+        swo[i] = k < C ? P.wo[c * C + k] : 0.0f;
+    }
+    for (int i = tid; i < 64; i += SF_THREADS) skt[i] = P.kt[i >> 3][i & 7];
+    for (int i = tid; i < 49; i += SF_THREADS) skc[i] = P.kc[i / 7][i % 7];
+    if (P.use_tma) {
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
+    __syncthreads();
+
+    // ---- stage A: last cascade level on the fly, then the two 1x1 layers (+ stabiliser on the tile itself), on the
+    // RH x RW region, 3 positions per thread
+    const int nA = RH * RW;
+    for (int base = 0; base < nA; base += 3 * SF_THREADS) {
+        float x[3][CINP], o[3][C];
+        int pos[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int pp = base + q * SF_THREADS + tid;
+            pos[q] = pp;
+            const int ppc = pp < nA ? pp : nA - 1;
+            const int py = ppc / RW, px = ppc - py * RW;
+            const int gy = clampi(Y0 + py, 0, H - 1), gx = clampi(X0 + px, 0, W - 1);
+#pragma unroll
+            for (int ci = 0; ci < CINP; ci++) x[q][ci] = 0.0f;
+            {
+                // channel 0: conv2d(latent, kron 7x7, zero padding) + latent   (upsampling.py:189-196)
+                const int8_t *lp = Lt + (gy - 3 - ly0) * LW + (gx - 3 - lx0);
+                float acc = 0.0f;
+#pragma unroll
+                for (int a = 0; a < 7; a++)
+#pragma unroll
+                    for (int b = 0; b < 7; b++) acc = __fmaf_rn(skc[a * 7 + b], (float)lp[a * LW + b], acc);
+                x[q][0] = __fadd_rn(acc, (float)lp[3 * LW + 3]);
+            }
+            {
+                // channels 1 .. cc: transposed conv (8x8 kron, stride 2, replicate-padded input, crop 11) of the
+                // coarser stack (upsampling.py:312-325): output (u, v) reads a 4 x 4 window, taps by parity
+                const int du = gy & 1, dv = gx & 1, qy = gy >> 1, qx = gx >> 1;
+                int ro[4], co[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    ro[t] = (clampi(qy - 2 + du + t, 0, ch - 1) - sy0) * SW;
+                    co[t] = clampi(qx - 2 + dv + t, 0, cw - 1) - sx0;
+                }
+#pragma unroll
+                for (int c = 0; c < CINP - 1; c++) {
+                    if (c < cc) {
+                        const float *sp = St + c * SH * SW;
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int t1 = 0; t1 < 4; t1++)
+#pragma unroll
+                            for (int t2 = 0; t2 < 4; t2++)
+                                acc = __fmaf_rn(skt[((1 - du) + 6 - 2 * t1) * 8 + (1 - dv) + 6 - 2 * t2], sp[ro[t1] + co[t2]], acc);
+                        x[q][c + 1] = acc;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) o[q][c] = sb1[c];
+        }
+        for (int hh = 0; hh < hid; hh++) {
+            float wv[CINP];
+#pragma unroll
+            for (int v = 0; v < CINP / 4; v++) {
+                const float4 t = *reinterpret_cast<const float4 *>(sw0 + hh * CINP + 4 * v);
+                wv[4 * v] = t.x; wv[4 * v + 1] = t.y; wv[4 * v + 2] = t.z; wv[4 * v + 3] = t.w;
+            }
+            float w1v[CP];
+#pragma unroll
+            for (int v = 0; v < CP / 4; v++) {
+                const float4 t = *reinterpret_cast<const float4 *>(sw1 + hh * CP + 4 * v);
+                w1v[4 * v] = t.x; w1v[4 * v + 1] = t.y; w1v[4 * v + 2] = t.z; w1v[4 * v + 3] = t.w;
+            }
+            const float bb = sb0[hh];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float a = bb;
+#pragma unroll
+                for (int ci = 0; ci < CINP; ci++)
+                    if (ci < cin) a = __fmaf_rn(wv[ci], x[q][ci], a);
+                if (P.relu0) a = fmaxf(a, 0.0f);
+#pragma unroll
+                for (int c = 0; c < C; c++) o[q][c] = __fmaf_rn(w1v[c], a, o[q][c]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            if (pos[q] >= nA) continue;
+            const int py = pos[q] / RW, px = pos[q] - py * RW;
+#pragma unroll
+            for (int c = 0; c < C; c++) bufA[(c * RH + py) * RW + px] = P.relu1 ? fmaxf(o[q][c], 0.0f) : o[q][c];
+            const int ty = py - n3, tx = px - n3;
+            if (P.stab_in && ty >= 0 && ty < SF_TH && tx >= 0 && tx < SF_TW) {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float a = sbs[c];
+#pragma unroll
+                    for (int ci = 0; ci < CINP; ci++)
+                        if (ci < P.stab_in) a = __fmaf_rn(sws[c * CINP + ci], x[q][ci], a);
+                    sstab[(c * SF_TH + ty) * SF_TW + tx] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 3x3 layers, shared memory -> shared memory (the last one -> registers -> output)
+    const float *cur = bufA;
+    int cwid = RW, chh = RH, off = n3;
+    for (int l = 0; l < n3 - 1; l++) {
+        const int ow = cwid - 2, oh = chh - 2;
+        const float *wl = sw3 + l * C * C * 9;
+        for (int pp = tid; pp < ow * oh; pp += SF_THREADS) {
+            const int py = pp / ow, px = pp - py * ow;
+            const int gy = clampi(y0 - (off - 1) + py, 0, H - 1), gx = clampi(x0 - (off - 1) + px, 0, W - 1);
+            const int by = gy - (y0 - off), bx = gx - (x0 - off);
+            float acc[C];
+#pragma unroll
+            for (int co = 0; co < C; co++) acc[co] = sb3[l * CP + co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++)
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        const float v = cur[(ci * chh + by + ky - 1) * cwid + bx + kx - 1];
+#pragma unroll
+                        for (int co = 0; co < C; co++) acc[co] = __fmaf_rn(wl[((co * C + ci) * 3 + ky) * 3 + kx], v, acc[co]);
+                    }
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                float a = acc[co];
+                if (P.res3[l]) a = __fadd_rn(a, cur[(co * chh + by) * cwid + bx]);
+                if (P.relu3[l]) a = fmaxf(a, 0.0f);
+                bufB[(co * oh + py) * ow + px] = a;
+            }
+        }
+        __syncthreads();
+        cur = bufB;
+        cwid = ow;
+        chh = oh;
+        off -= 1;
+    }
+    // ---- last stage on the tile: last 3x3 layer (if any), + stabiliser, output transform, frame tail, store
+    const size_t plane = (size_t)H * W;
+    const float M = P.M;
+    // 4:2:0 tail: rounded U, V samples of the tile [2][SF_TH][SF_TW], kept where the stabiliser output was (every
+    // thread has read its own position of it before it writes there)
+    float *uvq = sstab;
+    for (int pp = tid; pp < SF_TW * SF_TH; pp += SF_THREADS) {
+        const int ty = pp / SF_TW, tx = pp - ty * SF_TW;
+        const int gy = y0 + ty, gx = x0 + tx;
+        const bool inside = gy < H && gx < W;
+        const int by = (inside ? ty : 0) + off, bx = (inside ? tx : 0) + off;
+        float t[C];
+        if (n3 > 0) {
+            const int l = n3 - 1;
+            const float *wl = sw3 + l * C * C * 9;
+#pragma unroll
+            for (int co = 0; co < C; co++) t[co] = sb3[l * CP + co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++)
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        const float v = cur[(ci * chh + by + ky - 1) * cwid + bx + kx - 1];
+#pragma unroll
+                        for (int co = 0; co < C; co++) t[co] = __fmaf_rn(wl[((co * C + ci) * 3 + ky) * 3 + kx], v, t[co]);
+                    }
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                if (P.res3[l]) t[co] = __fadd_rn(t[co], cur[(co * chh + by) * cwid + bx]);
+                if (P.relu3[l]) t[co] = fmaxf(t[co], 0.0f);
+            }
+        } else {
+#pragma unroll
+            for (int co = 0; co < C; co++) t[co] = cur[(co * chh + by) * cwid + bx];
+        }
+        if (P.stab_in) {
+#pragma unroll
+            for (int co = 0; co < C; co++) t[co] = __fadd_rn(t[co], sstab[(co * SF_TH + (inside ? ty : 0)) * SF_TW + (inside ? tx : 0)]);
+        }
+        float ov[C];
+#pragma unroll
+        for (int co = 0; co < C; co++) {
+            float a = sbo[co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++) a = __fmaf_rn(swo[co * CP + ci], t[ci], a);
+            ov[co] = a;
+        }
+        if (P.finish == 0) {
+            if (inside) {
+#pragma unroll
+                for (int co = 0; co < C; co++) P.out[co][(size_t)gy * W + gx] = ov[co];
+            }
+        } else if (P.finish == 1) {
+            if (inside) {
+#pragma unroll
+                for (int co = 0; co < C; co++) P.out[co][(size_t)gy * W + gx] = quant(clamp01(quant(ov[co], M)), M);
+            }
+        } else {
+            if (inside) P.out[0][(size_t)gy * W + gx] = quant(clamp01(quant(ov[0], M)), M);
+            uvq[(0 * SF_TH + ty) * SF_TW + tx] = quant(ov[1 < C ? 1 : 0], M);
+            uvq[(1 * SF_TH + ty) * SF_TW + tx] = quant(ov[2 < C ? 2 : 0], M);
+        }
+    }
+    (void)plane;
+    if (P.finish == 2) {
+        __syncthreads();
+        // 2 x 2 average of the rounded chroma samples in the order of the reference's avg_pool2d loop, clamp, round
+        const int h2 = H / 2, w2 = W / 2;
+        for (int pp = tid; pp < 2 * (SF_TW / 2) * (SF_TH / 2); pp += SF_THREADS) {
+            const int c = pp / ((SF_TW / 2) * (SF_TH / 2)), r = pp - c * (SF_TW / 2) * (SF_TH / 2);
+            const int by = r / (SF_TW / 2), bx = r - by * (SF_TW / 2);
+            const int y2 = y0 / 2 + by, x2 = x0 / 2 + bx;
+            if (y2 >= h2 || x2 >= w2) continue;
+            const float *q = uvq + (c * SF_TH + 2 * by) * SF_TW + 2 * bx;
+            float s = 0.0f;
+            s = __fadd_rn(s, q[0]);
+            s = __fadd_rn(s, q[1]);
+            s = __fadd_rn(s, q[SF_TW]);
+            s = __fadd_rn(s, q[SF_TW + 1]);
+            P.out[1 + c][(size_t)y2 * w2 + x2] = quant(clamp01(__fdiv_rn(s, 4.0f)), M);
+        }
+    }
+}
+
 __global__ void k_add(float *__restrict__ a, const float *__restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = __fadd_rn(a[i], b[i]);
@@ -674,6 +1124,149 @@ int ccd_syn_fused(const float *d_in, int h, int w, int cin, const SynLayerDev *l
     SF_CASE(8, 2); SF_CASE(8, 3); SF_CASE(8, 4); SF_CASE(8, 5);
     SF_CASE(16, 2); SF_CASE(16, 3); SF_CASE(16, 4); SF_CASE(16, 5);
 #undef SF_CASE
+    return -1;
+}
+
+// ---- batched float tail: host side -----------------------------------------------------------------------
+size_t ccd_tail_job_bytes(void) { return sizeof(TailSynJob); }
+size_t ccd_tail_level_job_bytes(void) { return sizeof(UpsLevelJob); }
+
+void ccd_tail_fill_level(void *dst, const int8_t *lat, const float *in, const int8_t *in8, float *out, int cc, int ch,
+                         int cw, int th, int tw, const float *wt1d, const float *wc1d) {
+    UpsLevelJob J;
+    memset(&J, 0, sizeof(J));
+    J.lat = lat; J.in = in; J.in8 = in8; J.out = out; J.cc = cc; J.ch = ch; J.cw = cw; J.th = th; J.tw = tw;
+    for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 8; b++) {
+            volatile float k = wt1d[a] * wt1d[b];  // one rounded fp32 product, no contraction
+            J.kt[a][b] = k;
+        }
+    for (int a = 0; a < 7; a++)
+        for (int b = 0; b < 7; b++) {
+            volatile float k = wc1d[a] * wc1d[b];
+            J.kc[a][b] = k;
+        }
+    memcpy(dst, &J, sizeof(J));
+}
+
+int ccd_tail_launch_level(const void *d_jobs, int n_jobs, int planes, int max_tw, int max_th, cudaStream_t st) {
+    const dim3 grid((max_tw + 31) / 32, (max_th + 7) / 8, (unsigned)(n_jobs * planes));
+    k_ups_level_b<<<grid, kBlock2, 0, st>>>(reinterpret_cast<const UpsLevelJob *>(d_jobs), planes);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+namespace {
+typedef int (*PFN_encodeTiled)(void *tensorMap, int dataType, unsigned rank, void *globalAddress, const uint64_t *globalDim,
+                               const uint64_t *globalStrides, const uint32_t *boxDim, const uint32_t *elementStrides,
+                               int interleave, int swizzle, int l2Promotion, int oobFill);
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+}  // namespace
+
+// Fills one TailSynJob (host memory).  Returns 1 when the tiles are staged with TMA, 0 when with plain loads
+// (pitches / addresses that cuTensorMapEncodeTiled does not take), < 0 when the architecture is outside the family.
+int ccd_tail_fill_syn(void *dst, const CcdTailSynDesc &T) {
+    const int n_layers = T.n_layers;
+    if (n_layers < 2 || n_layers > 4) return -1;
+    const SynLayerDev &L0 = T.layers[0], &L1 = T.layers[1];
+    const int C = L1.cout;
+    if (L0.k != 1 || L1.k != 1 || L0.residual || L1.residual || T.cin > 16 || T.cin < 2 || L0.cout > 256 || C < 2 || C > 5) return -1;
+    if (T.ot.cin != C || T.ot.cout != C) return -1;
+    for (int l = 2; l < n_layers; l++)
+        if (T.layers[l].k != 3 || T.layers[l].cin != C || T.layers[l].cout != C) return -1;
+    if (T.stab && (T.stab->cin > T.cin || T.stab->cout != C)) return -1;
+    TailSynJob J;
+    memset(&J, 0, sizeof(J));
+    J.lat = T.lat; J.stk = T.stk; J.stk8 = T.stk8;
+    for (int c = 0; c < 5; c++) J.out[c] = T.out[c];
+    J.h = T.h; J.w = T.w; J.ch = T.ch; J.cw = T.cw; J.cin = T.cin; J.hid = L0.cout; J.n3 = n_layers - 2;
+    J.relu0 = L0.relu; J.relu1 = L1.relu;
+    for (int l = 0; l < 2; l++) {
+        const bool on = l < J.n3;
+        J.res3[l] = on ? T.layers[2 + l].residual : 0;
+        J.relu3[l] = on ? T.layers[2 + l].relu : 0;
+        J.w3[l] = on ? T.layers[2 + l].w : nullptr;
+        J.b3[l] = on ? T.layers[2 + l].b : nullptr;
+    }
+    J.stab_in = T.stab ? T.stab->cin : 0;
+    J.w0 = L0.w; J.b0 = L0.b; J.w1 = L1.w; J.b1 = L1.b;
+    J.ws = T.stab ? T.stab->w : nullptr; J.bs = T.stab ? T.stab->b : nullptr;
+    J.wo = T.ot.w; J.bo = T.ot.b;
+    J.finish = T.finish;
+    J.M = T.M;
+    for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 8; b++) {
+            volatile float k = T.wt1d[a] * T.wt1d[b];
+            J.kt[a][b] = k;
+        }
+    for (int a = 0; a < 7; a++)
+        for (int b = 0; b < 7; b++) {
+            volatile float k = T.wc1d[a] * T.wc1d[b];
+            J.kc[a][b] = k;
+        }
+    // TMA descriptors (CU_TENSOR_MAP_DATA_TYPE_UINT8 = 0, FLOAT32 = 7; no interleave, no swizzle, L2 promotion 128 B,
+    // out-of-bounds elements read as zero)
+    J.use_tma = 0;
+    PFN_encodeTiled enc = get_encode_tiled();
+    const int cc = T.cin - 1;
+    if (enc && T.allow_tma && !T.stk8 && (T.w % 16) == 0 && (T.cw % 4) == 0 && (reinterpret_cast<uintptr_t>(T.lat) % 16) == 0 &&
+        (reinterpret_cast<uintptr_t>(T.stk) % 16) == 0) {
+        const uint64_t gd0[2] = {(uint64_t)T.w, (uint64_t)T.h};
+        const uint64_t gs0[1] = {(uint64_t)T.w};
+        const uint32_t bx0[2] = {(uint32_t)ts_lw(J.n3), (uint32_t)ts_lh(J.n3)};
+        const uint32_t es[3] = {1, 1, 1};
+        const uint64_t gd1[3] = {(uint64_t)T.cw, (uint64_t)T.ch, (uint64_t)cc};
+        const uint64_t gs1[2] = {(uint64_t)T.cw * 4, (uint64_t)T.cw * 4 * (uint64_t)T.ch};
+        const uint32_t bx1[3] = {(uint32_t)ts_sw(J.n3), (uint32_t)ts_sh(J.n3), (uint32_t)cc};
+        const int r0 = enc(J.tmap_lat, 0, 2, const_cast<int8_t *>(T.lat), gd0, gs0, bx0, es, 0, 0, 1, 0);
+        const int r1 = enc(J.tmap_stk, 7, 3, const_cast<float *>(T.stk), gd1, gs1, bx1, es, 0, 0, 1, 0);
+        J.use_tma = (r0 == 0 && r1 == 0) ? 1 : 0;
+    }
+    memcpy(dst, &J, sizeof(J));
+    return J.use_tma;
+}
+
+template <int CINP, int C>
+static int launch_tail_syn(const void *d_jobs, int n_jobs, int n3_max, int hid_max, int max_w, int max_h, cudaStream_t st) {
+    constexpr int CP = (C + 3) & ~3;
+    const int RW = SF_TW + 2 * n3_max, RH = SF_TH + 2 * n3_max;
+    size_t bytes = 128 + (((size_t)ts_lw(n3_max) * ts_lh(n3_max) + 127) & ~(size_t)127);
+    size_t fl = (((size_t)(CINP - 1) * ts_sh(n3_max) * ts_sw(n3_max) + 31) & ~(size_t)31);
+    fl += (size_t)hid_max * CINP + hid_max + (size_t)hid_max * CP + CP + 2 * C * C * 9 + 2 * CP + C * CINP + CP + C * CP + CP + 64 + 52;
+    fl += (size_t)C * RH * RW + (n3_max == 2 ? (size_t)C * (RH - 2) * (RW - 2) : 0) + (size_t)C * SF_TH * SF_TW;
+    const size_t smem = bytes + fl * sizeof(float);
+    auto kern = k_tail_syn<CINP, C>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const dim3 grid((max_w + SF_TW - 1) / SF_TW, (max_h + SF_TH - 1) / SF_TH, (unsigned)n_jobs);
+    kern<<<grid, SF_THREADS, smem, st>>>(reinterpret_cast<const TailSynJob *>(d_jobs));
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
+// all jobs of one launch share (cinp, C); n3 / hid / sizes may differ (shared memory sized for the maxima)
+int ccd_tail_launch_syn(const void *d_jobs, int n_jobs, int cinp, int C, int n3_max, int hid_max, int max_w, int max_h,
+                        cudaStream_t st) {
+#define TS_CASE(CI, CC) if (cinp == CI && C == CC) return launch_tail_syn<CI, CC>(d_jobs, n_jobs, n3_max, hid_max, max_w, max_h, st)
+    TS_CASE(4, 2); TS_CASE(4, 3); TS_CASE(4, 4); TS_CASE(4, 5);
+    TS_CASE(8, 2); TS_CASE(8, 3); TS_CASE(8, 4); TS_CASE(8, 5);
+    TS_CASE(16, 2); TS_CASE(16, 3); TS_CASE(16, 4); TS_CASE(16, 5);
+#undef TS_CASE
     return -1;
 }
 

@@ -60,6 +60,34 @@ def write_yuv(data, bitdepth: int, frame_data_type: str, file_path: str, norm: b
         out.tofile(f_out)
 
 
+# ---- writers of samples already packed on the device (ccd_pack_frame): no arithmetic left on the host ----------
+def write_packed_yuv(planar: np.ndarray, bitdepth: int, frame_data_type: str, file_path: str, append: bool) -> None:
+    assert frame_data_type in ["yuv420", "yuv444"], (
+        f"Found incorrect datatype in write_yuv() function: {frame_data_type}. "
+        'Data type should be "yuv420" or "yuv444".'
+    )
+    # io/format/yuv.py:157: 2-byte samples only when bitdepth == 10, 1-byte otherwise (kept as is)
+    dtype = np.uint16 if bitdepth == 10 else np.uint8
+    out = planar if planar.dtype == dtype else planar.astype(np.int64).astype(dtype)
+    with open(file_path, "ab" if append else "wb") as f_out:
+        out.tofile(f_out)
+
+
+def write_packed_ppm(hwc: np.ndarray, bitdepth: int, file_path: str) -> None:
+    h, w = hwc.shape[:2]
+    max_val = 2**bitdepth - 1
+    body = hwc.astype(np.uint8 if max_val <= 255 else ">u2").tobytes()
+    with open(file_path, "wb") as f_out:
+        f_out.write(f"P6\n{w} {h}\n{max_val}\n".encode("ascii"))
+        f_out.write(body)
+
+
+def write_packed_png(hwc_u8: np.ndarray, file_path: str) -> None:
+    from PIL import Image
+
+    Image.fromarray(np.ascontiguousarray(hwc_u8), mode="RGB").save(file_path)
+
+
 def save_frame_data_to_file(frame_data: FrameData, file_path: str, append: bool = False) -> None:
     ext = os.path.splitext(file_path)[1]
     assert ext in POSSIBLE_EXT, (

@@ -98,7 +98,11 @@ int64_t ccd_decode_nn(const CcdCoolChicDesc *desc, const uint8_t *nn_bytes, size
 /* One independent Cool-chic to decode.  d_out: float32 [C_out][img_h][img_w] raw synthesis
  * output (un-clamped, un-rounded -- what encode_decode_coolchic returns).  d_latents
  * (optional, may be NULL): int8 decoded latents in decode order (coarsest grid first, each
- * grid row-major).  status (out): per-job status written on completion. */
+ * grid row-major).  status (out): per-job status written on completion.
+ * Frame tail (optional, the Cool-chic of an I frame): finish_bitdepth != 0 asks for decode_frame's
+ * round / (4:2:0 average) / clamp / round (bitstream/decode.py:191-206) fused into the synthesis
+ * kernel's epilogue: d_out then receives the FINISHED frame -- [3][H][W] for finish_type 0 (rgb),
+ * 2 (yuv444), 3 (flow); for finish_type 1 (yuv420) d_out = y [H][W], d_out_u, d_out_v [H/2][W/2]. */
 typedef struct CcdJob {
     const CcdCoolChicDesc *desc;
     const uint8_t *nn_bytes;
@@ -108,6 +112,10 @@ typedef struct CcdJob {
     float *d_out;
     int8_t *d_latents;
     int32_t status;
+    int32_t finish_bitdepth;
+    int32_t finish_type;
+    float *d_out_u;
+    float *d_out_v;
 } CcdJob;
 
 /* Decode n independent Cool-chics concurrently (one persistent CTA per stream for the
