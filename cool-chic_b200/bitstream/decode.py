@@ -107,44 +107,26 @@ def output_shape(header: CoolChicHeader) -> Tuple[int, int, int, int]:
     return (1, c, int(p.img_size[0]), int(p.img_size[1]))
 
 
-def _decode_all_coolchics(parsed, device: int, decode_fn=None) -> List[Dict[str, torch.Tensor]]:
-    """Pass 1 of decode_video: every Cool-chic of every frame.  Single process: one concurrent batch.
-    Under torch.distributed (SURVEY 8e / BASELINE configs[4]): Cool-chic i of the flattened list is decoded by
-    rank i mod world, then broadcast from its owner, so every rank holds every raw output and
-    reconstructs the GOP itself (the reconstruction is a few elementwise kernels)."""
-    import torch.distributed as dist
-
-    from ..dist import shard_indices
-
+def _decode_all_coolchics(parsed, device: int, decode_fn=None, frames_mine=None) -> List[Dict[str, torch.Tensor]]:
+    """Pass 1 of decode_video: the Cool-chics of the frames in ``frames_mine`` (all frames by default), one
+    concurrent batch (one persistent CTA per stream).  Under torch.distributed a rank only decodes the Cool-chics
+    of the frames it OWNS (see decode_video_bytes)."""
+    single = decode_fn is None
     decode_fn = decode_fn or decode_coolchics
-    flat = [(i, name) for i, (_, ccs) in enumerate(parsed) for name in ccs]
+    if frames_mine is None:
+        frames_mine = range(len(parsed))
+    flat = [(i, name) for i in frames_mine for name in parsed[i][1]]
     hdr = [parsed[i][1][n][0] for i, n in flat]
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
-    mine = shard_indices(len(flat), rank, world)
-    fins = [None] * len(flat)
-    if world == 1 and decode_fn is decode_coolchics:
-        for k, (i, name) in enumerate(flat):
-            if name == "residue":
-                fins[k] = _finish_request(parsed[i][0], parsed[i][1])
-        outs_mine = decode_fn([hdr[k] for k in mine], [parsed[flat[k][0]][1][flat[k][1]][1] for k in mine],
-                              [parsed[flat[k][0]][1][flat[k][1]][2] for k in mine], device=device,
-                              finish=[fins[k] for k in mine])
-    else:
-        outs_mine = decode_fn([hdr[k] for k in mine], [parsed[flat[k][0]][1][flat[k][1]][1] for k in mine],
-                              [parsed[flat[k][0]][1][flat[k][1]][2] for k in mine], device=device)
-    outs: List[Optional[torch.Tensor]] = [None] * len(flat)
-    for k, o in zip(mine, outs_mine):
-        outs[k] = o
-    if world > 1:
-        ref = outs_mine[0] if outs_mine else None
-        for k in range(len(flat)):
-            owner = k % world
-            if outs[k] is None:
-                dev = ref.device if ref is not None else (torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu"))
-                outs[k] = torch.empty(output_shape(hdr[k]), dtype=torch.float32, device=dev)
-            dist.broadcast(outs[k], src=owner)
     cc_out: List[Dict[str, torch.Tensor]] = [dict() for _ in parsed]
+    if not flat:
+        return cc_out
+    args = ([hdr[k] for k in range(len(flat))], [parsed[i][1][n][1] for i, n in flat], [parsed[i][1][n][2] for i, n in flat])
+    if single:
+        fins = [_finish_request(parsed[i][0], parsed[i][1]) if n == "residue" else None for i, n in flat]
+        outs = decode_fn(*args, device=device, finish=fins)
+    else:
+        fins = [None] * len(flat)
+        outs = decode_fn(*args, device=device)
     for k, ((i, name), o) in enumerate(zip(flat, outs)):
         cc_out[i][name] = o
         if fins[k] is not None:
@@ -152,14 +134,31 @@ def _decode_all_coolchics(parsed, device: int, decode_fn=None) -> List[Dict[str,
     return cc_out
 
 
+def _frame_planes(fd: FrameData) -> List[torch.Tensor]:
+    return [fd.data[k] for k in ("y", "u", "v")] if fd.frame_data_type == "yuv420" else [fd.data]
+
+
+def _empty_like_frame(frame_header: FrameHeader, img_size, dev) -> FrameData:
+    """Receive buffer for a frame reconstructed by another rank (same layout as the owner's FrameData)."""
+    h, w = img_size
+    fmt, b = frame_header.get_value("frame_data_type"), frame_header.get_value("bitdepth")
+    if fmt == "yuv420":
+        data = {"y": torch.empty((1, 1, h, w), dtype=torch.float32, device=dev),
+                "u": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=dev),
+                "v": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=dev)}
+    else:
+        data = torch.empty((1, 3, h, w), dtype=torch.float32, device=dev)
+    return FrameData(bitdepth=b, frame_data_type=fmt, data=data)
+
+
 @torch.no_grad()
 def decode_video_bytes(bitstream_bytes: bytes, decoded_path: Optional[str] = None, max_decoding_order: int = -1,
                        verbosity: int = 0, device: int = 0, output_device: str = "cpu", decode_fn=None,
                        reconstruct_fn=None) -> Dict[str, FrameData]:
     """decode_video on bytes already in memory.  With an initialised torch.distributed process group every
-    rank must call it with the same bytes (see dist.broadcast_byte_strings): the Cool-chics are sharded over
-    the ranks, every rank returns all frames.  ``decode_fn`` / ``reconstruct_fn`` exist for the CPU (gloo)
-    test of the plumbing."""
+    rank must call it with the same bytes (see dist.broadcast_byte_strings): the frames are dealt to the ranks
+    (frame ownership), reconstructed frames are exchanged, every rank returns all frames.  ``decode_fn`` /
+    ``reconstruct_fn`` exist for the CPU (gloo) test of the plumbing."""
     reconstruct_fn = reconstruct_fn or _reconstruct
     bitstream_bytes = memoryview(bitstream_bytes)  # every "remaining bytes" below is a view, not a copy
     video_header = VideoHeader()
@@ -171,13 +170,35 @@ def decode_video_bytes(bitstream_bytes: bytes, decoded_path: Optional[str] = Non
     if max_decoding_order == -1:
         max_decoding_order = coding_structure.get_max_coding_order()
 
-    # ---- pass 1: parse every frame, decode ALL Cool-chics concurrently on the device(s)
+    # ---- pass 1: parse every frame, decode the Cool-chics concurrently on the device(s).
+    # Multi-GPU (BASELINE configs[4]): FRAME OWNERSHIP -- frame i (coding order) belongs to rank
+    # i mod world; a rank entropy-decodes and synthesises only the Cool-chics of its own frames (they need no
+    # reference), reconstructs its frames when their references have arrived, and broadcasts each RECONSTRUCTED
+    # frame (the only exchange of the path: one NCCL broadcast per plane, 12.4 MB for a 1080p 4:2:0 frame).
+    import torch.distributed as dist
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
     t0 = time.time()
     parsed = []
     for coding_idx in range(max_decoding_order + 1):
         frame_header, ccs, bitstream_bytes = _parse_frame(bitstream_bytes)
         parsed.append((frame_header, ccs))
-    cc_out = _decode_all_coolchics(parsed, device, decode_fn)
+    owner = [i % world for i in range(len(parsed))]
+    mine = [i for i in range(len(parsed)) if owner[i] == rank]
+    err = None
+    try:
+        cc_out = _decode_all_coolchics(parsed, device, decode_fn, frames_mine=mine if world > 1 else None)
+    except Exception as e:  # noqa: BLE001 -- re-raised on EVERY rank below: nobody is left waiting in a broadcast
+        err, cc_out = e, None
+    if world > 1:
+        dev0 = torch.device("cuda", device) if torch.cuda.is_available() and dist.get_backend() == "nccl" else torch.device("cpu")
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=dev0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) != 0:
+            raise err if err is not None else RuntimeError("decode_video: a Cool-chic failed to decode on another rank")
+    elif err is not None:
+        raise err
     t_cc = (time.time() - t0) / max(1, len(parsed))
 
     # ---- pass 2: reconstruct in coding order (references looked up by display index)
@@ -188,9 +209,26 @@ def decode_video_bytes(bitstream_bytes: bytes, decoded_path: Optional[str] = Non
             print(frame_header.pretty_string())
             for n in ccs:
                 print(ccs[n][0].pretty_string())
-        refs_data = [coding_structure.get_frame_from_display_order(idx_ref).data for idx_ref in frame.index_references]
-        frame.set_frame_data(reconstruct_fn(frame_header, cc_out[coding_idx], refs_data, device))
-        cc_out[coding_idx] = None
+        if owner[coding_idx] == rank:
+            refs_data = [coding_structure.get_frame_from_display_order(idx_ref).data for idx_ref in frame.index_references]
+            fd = reconstruct_fn(frame_header, cc_out[coding_idx], refs_data, device)
+            cc_out[coding_idx] = None
+        else:
+            p = ccs["residue"][0].get_coolchic_parameter()
+            any_local = next((f for f in (coding_structure.get_frame_from_coding_order(k) for k in range(coding_idx))
+                              if f.data is not None), None)
+            dev = _frame_planes(any_local.data)[0].device if any_local is not None else (
+                torch.device("cuda", device) if torch.cuda.is_available() else torch.device("cpu"))
+            fd = _empty_like_frame(frame_header, (int(p.img_size[0]), int(p.img_size[1])), dev)
+        if world > 1:
+            if reconstruct_fn is _reconstruct:
+                for t in _frame_planes(fd):
+                    dist.broadcast(t, src=owner[coding_idx])
+            else:  # stand-in reconstruct functions of the CPU test: ship whatever they return
+                box = [fd if owner[coding_idx] == rank else None]
+                dist.broadcast_object_list(box, src=owner[coding_idx])
+                fd = box[0]
+        frame.set_frame_data(fd)
         if torch.cuda.is_available():
             torch.cuda.synchronize(device)
         print(f"Decoding frame {frame.display_order:<4} time = {time.time() - start_time + t_cc:6.2f} seconds.")

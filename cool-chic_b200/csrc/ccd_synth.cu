@@ -14,6 +14,7 @@
 // every output is acc = init; for ci, for ky, for kx: acc = fmaf(w, x, acc).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ccd_detmath.h"
@@ -534,11 +535,11 @@ struct alignas(64) TailSynJob {
     const float *ws, *bs, *wo, *bo;
     float kt[8][8], kc[7][7];
 };
-constexpr int TS_LW_MAX = 48, TS_LH_MAX = SF_TH + 4 + 6;              // int8 latent tile (n3 <= 2)
-constexpr int TS_SW_MAX = 24, TS_SH_MAX = (SF_TH + 4) / 2 + 5;        // half-resolution stack tile
-__host__ __device__ inline int ts_lw(int n3) { return (SF_TW + 2 * n3 + 6 + 15) & ~15; }
+// (TMA needs the box to start on a 16-byte boundary in the innermost dimension: the tile origins are rounded down
+// to a multiple of 16 int8 / 4 fp32 columns and the boxes widened accordingly)
+__host__ __device__ inline int ts_lw(int n3) { return (SF_TW + 2 * n3 + 6 + 15 + 15) & ~15; }
 __host__ __device__ inline int ts_lh(int n3) { return SF_TH + 2 * n3 + 6; }
-__host__ __device__ inline int ts_sw(int n3) { return ((SF_TW + 2 * n3) / 2 + 5 + 3) & ~3; }
+__host__ __device__ inline int ts_sw(int n3) { return ((SF_TW + 2 * n3) / 2 + 5 + 3 + 3) & ~3; }
 __host__ __device__ inline int ts_sh(int n3) { return (SF_TH + 2 * n3) / 2 + 5; }
 
 __device__ __forceinline__ float quant(float v, float M);
@@ -577,8 +578,8 @@ __global__ void __launch_bounds__(SF_THREADS) k_tail_syn(const TailSynJob *__res
     const int tid = threadIdx.x;
     // tile origins (frame coordinates of element 0 of the tiles)
     const int Y0 = y0 - n3, X0 = x0 - n3;                   // stage-A region
-    const int ly0 = Y0 - 3, lx0 = X0 - 3;                   // latent tile
-    const int sy0 = ((Y0 < 0 ? 0 : Y0) >> 1) - 2, sx0 = ((X0 < 0 ? 0 : X0) >> 1) - 2;  // stack tile
+    const int ly0 = Y0 - 3, lx0 = (X0 - 3) & ~15;           // latent tile (16-byte aligned start)
+    const int sy0 = ((Y0 < 0 ? 0 : Y0) >> 1) - 2, sx0 = (((X0 < 0 ? 0 : X0) >> 1) - 2) & ~3;  // stack tile
     const int ch = P.ch, cw = P.cw;
     // ---- stage 0: tiles -> shared memory
     if (P.use_tma) {
@@ -593,8 +594,10 @@ __global__ void __launch_bounds__(SF_THREADS) k_tail_syn(const TailSynJob *__res
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
             const uint64_t tm0 = reinterpret_cast<uint64_t>(P.tmap_lat), tm1 = reinterpret_cast<uint64_t>(P.tmap_stk);
             // the descriptors live in global memory (one pair per stream of the launch, written by the host)
-            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm0) : "memory");
-            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm1) : "memory");
+            if (P.use_tma & 2) {
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm0) : "memory");
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm1) : "memory");
+            }
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                 ::"r"((uint32_t)__cvta_generic_to_shared(Lt)), "l"(tm0), "r"(lx0), "r"(ly0), "r"(bar_a)
@@ -1233,7 +1236,11 @@ int ccd_tail_fill_syn(void *dst, const CcdTailSynDesc &T) {
         const uint32_t bx1[3] = {(uint32_t)ts_sw(J.n3), (uint32_t)ts_sh(J.n3), (uint32_t)cc};
         const int r0 = enc(J.tmap_lat, 0, 2, const_cast<int8_t *>(T.lat), gd0, gs0, bx0, es, 0, 0, 1, 0);
         const int r1 = enc(J.tmap_stk, 7, 3, const_cast<float *>(T.stk), gd1, gs1, bx1, es, 0, 0, 1, 0);
-        J.use_tma = (r0 == 0 && r1 == 0) ? 1 : 0;
+        J.use_tma = (r0 == 0 && r1 == 0) ? 3 : 0;  // bit 0: TMA staging, bit 1: descriptor fence before the first use
+        if (J.use_tma) {
+            const char *e = getenv("CCD_TMA_MODE");  // development switch: 0 plain loads, 1 TMA, 3 TMA + descriptor fence
+            if (e) J.use_tma = atoi(e);
+        }
     }
     memcpy(dst, &J, sizeof(J));
     return J.use_tma;

@@ -56,7 +56,8 @@ def test_shard_indices_cover_everything():
 
 def _gop_worker(rank, world, port, ret):
     """decode_video_bytes under a 2-rank gloo group with stand-in decode / reconstruct functions: every rank
-    decodes only its share of the Cool-chics, and ends up with all of them after the broadcasts."""
+    decodes only the Cool-chics of the frames it owns, reconstructs those frames, and ends up with all frames
+    after the exchange of the reconstructed ones."""
     sys.path.insert(0, os.path.abspath(ROOT))
     import torch
     import torch.distributed as dist
@@ -89,7 +90,7 @@ def _gop_worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_gop_coolchics_are_sharded_and_broadcast():
+def test_gop_frames_are_owned_and_exchanged():
     import io
     from contextlib import redirect_stdout
 
@@ -97,7 +98,8 @@ def test_gop_coolchics_are_sharded_and_broadcast():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_gop_worker, args=(world, port, ret), nprocs=world, join=True)
-    # 5 frames: I (1 Cool-chic) + 4 inter frames (2 each) = 9 Cool-chics, split 5 / 4, no overlap
+    # 5 frames: I (1 Cool-chic) + 4 inter frames (2 each) = 9 Cool-chics; frame ownership by coding index:
+    # rank 0 owns frames 0, 2, 4 (1 + 2 + 2 Cool-chics), rank 1 frames 1, 3 (2 + 2), no overlap
     assert len(ret[0][0]) == 5 and len(ret[1][0]) == 4
     assert ret[0][1] == ret[1][1] and len(ret[0][1]) == 5  # both ranks reconstructed the same 5 frames
     # and the same values as a single-process run of the same stand-ins
