@@ -362,8 +362,21 @@ class CoolChicHeader(_Header):
         return out
 
     def get_coolchic_parameter(self) -> "CoolChicParameter":
-        """header.py:354-377."""
+        """header.py:354-377.  A corrupt header raises ValueError here (the reference fails later with whatever
+        exception the first impossible value triggers: ZeroDivisionError, IndexError ...)."""
         g = self.get_value
+        img = tuple(g("img_size"))
+        lat = tuple(g("latent_resolution"))
+        if len(img) != 2 or img[0] < 1 or img[1] < 1:
+            raise ValueError(f"Corrupt Cool-chic header: img_size = {img}")
+        if g("n_layer_synthesis") < 1:
+            raise ValueError("Corrupt Cool-chic header: n_layer_synthesis = 0")
+        if len(lat) != 2 or lat[0] > lat[1]:
+            raise ValueError(f"Corrupt Cool-chic header: latent_resolution = {lat}")
+        for key in ("ifce_resolution", "hyperlatent_resolution"):
+            r = g(key)
+            if r is not None and (len(r) != 2 or r[0] > r[1]):
+                raise ValueError(f"Corrupt Cool-chic header: {key} = {tuple(r)}")
         return CoolChicParameter(
             layers_synthesis=[g(f"syn_layer_{i}") for i in range(g("n_layer_synthesis"))],
             linear_stabiliser_synth=bool(g("linear_stabiliser_synth")),

@@ -143,6 +143,35 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+// Flag words of the hand-offs (progress, ready, done, the meta tags) are written with release and read with acquire
+// semantics at CTA scope: what a flag announces (window / hot entries, result words, decoded symbols) is visible to
+// the thread that saw the flag.  One exception, measured (tools/ab.sh): the coder's `done` store stays a plain volatile
+// store -- a release there is a fence in front of it on the serial chain's warp; it is ordered after the coder's own
+// result-word stores because shared-memory stores of one warp are performed in program order, and the helper reads
+// `done` with acquire.  (-DCCD_RELEASE_DONE makes it a release store.)
+__device__ __forceinline__ uint32_t lds_acq_u32(uint32_t a) {
+    uint32_t v;
+#ifdef CCD_RELAXED_FLAGS
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+#else
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+#endif
+    return v;
+}
+__device__ __forceinline__ void sts_rel_u32(uint32_t a, uint32_t v) {
+#ifdef CCD_RELAXED_FLAGS
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+#else
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void sts_done(uint32_t a, uint32_t v) {
+#ifdef CCD_RELEASE_DONE
+    sts_rel_u32(a, v);
+#else
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+#endif
+}
 __device__ __forceinline__ int lds_s8(uint32_t a) {
     int v;
     asm volatile("ld.volatile.shared.s8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -453,7 +482,7 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
     rel = __reduce_max_sync(0xffffffffu, rel);
     need = ord_diag + (uint32_t)rel;
     PROF_T(t0);
-    while ((int32_t)(lds_u32(sm.ctrl) - need) < 0) {
+    while ((int32_t)(lds_acq_u32(sm.ctrl) - need) < 0) {
 #ifdef CCD_SPIN_SLEEP
         __nanosleep(CCD_SPIN_SLEEP);
 #endif
@@ -548,8 +577,10 @@ __device__ __forceinline__ void produce_chunk(const SLoc &S, const SmemLayout &s
         const uint32_t out_off = (uint32_t)(g->lat_off + (long long)y * w + x);
         const uint32_t row_idx = (((uint32_t)y & row_mask) << 6) | ((uint32_t)x & (CCD_ROW_COLS - 1));
         // meta: x = output offset, y = row-ring index | (s_lo + 128) << 16, z = mu_idx | sc_idx << 16, w = tag
-        sts_v4(sm.meta + slot * 16u, make_uint4(out_off, row_idx | ((uint32_t)(s_lo + 128) << 16),
-                                                (uint32_t)mu_idx | ((uint32_t)sc_idx << 16), ord + 1u));
+        const uint32_t ma = sm.meta + slot * 16u;
+        sts_v2(ma, make_uint2(out_off, row_idx | ((uint32_t)(s_lo + 128) << 16)));
+        sts_u32(ma + 8u, (uint32_t)mu_idx | ((uint32_t)sc_idx << 16));
+        sts_rel_u32(ma + 12u, ord + 1u);  // the tag: everything this quad / thread stored for the symbol is visible before it
     }
     PROF_ADD(pc.win, t2);
 #ifdef CCD_PROFILE
@@ -858,7 +889,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     uint32_t o;
     uint4 a0, a1, a2, a3, b0, b1, b2, b3;
     auto refresh = [&]() {
-        const uint32_t r = lds_u32(ready_a);
+        const uint32_t r = lds_acq_u32(ready_a);
         limit = ((int32_t)(r - ord_end) > 0) ? ord_end : r;
     };
     auto advance_words = [&]() {  // the lane-held words move on (at most K words are consumed between two calls)
@@ -952,7 +983,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
         a3 = lds_v4(o + 48u);                                                                                         \
         CCD_T2_INLINE(j, hf_)                                                                                         \
         j++;                                                                                                          \
-        sts_u32(done_a, j);                                                                                           \
+        sts_done(done_a, j);                                                                                           \
         PROF_COUNT_RECOVER(f_);                                                                                       \
     }
 #ifdef CCD_PROFILE
@@ -983,7 +1014,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
                 D = Ds4;
                 R = Rs4;
                 j += K;
-                sts_u32(done_a, j);
+                sts_done(done_a, j);
 #ifdef CCD_PROFILE
                 pc.seg[3] += K;
 #endif
@@ -1006,7 +1037,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
                 }
             }
             j++;
-            sts_u32(done_a, j);
+            sts_done(done_a, j);
 #ifdef CCD_PROFILE
             pc.seg[4]++;
 #endif
@@ -1045,14 +1076,14 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
 #ifdef CCD_ONE_BLOCK
             // variant: one block per iteration (the steady loop needs 2 K ready symbols instead of 3 K), entries copied
             j += K;
-            sts_u32(done_a, j);
+            sts_done(done_a, j);
             a0 = b0;
             a1 = b1;
             a2 = b2;
             a3 = b3;
             continue;
 #endif
-            sts_u32(done_a, j + K);  // every lane stores the same word: no predicate on the hot path
+            sts_done(done_a, j + K);  // every lane stores the same word: no predicate on the hot path
             o = sm.hot + ((j + 2u * K) & ring_mask) * 16u;
             a0 = lds_v4(o);
             a1 = lds_v4(o + 16u);
@@ -1069,7 +1100,7 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
                 R = Rs4;
             }
             j += 2u * K;
-            sts_u32(done_a, j);
+            sts_done(done_a, j);
 #ifdef CCD_PROFILE
             pc.seg[3] += 2 * K;
 #endif
@@ -1097,17 +1128,17 @@ __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm,
         if (r != ord_end) {
             const uint32_t jj = r + (uint32_t)lane;
             bool ok = false;
-            if ((int32_t)(ord_end - jj) > 0) ok = lds_u32(sm.meta + (jj & ring_mask) * 16u + 12u) == jj + 1u;
+            if ((int32_t)(ord_end - jj) > 0) ok = lds_acq_u32(sm.meta + (jj & ring_mask) * 16u + 12u) == jj + 1u;
             const uint32_t b = __ballot_sync(0xffffffffu, ok);
             const uint32_t cnt = (b == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~b) - 1);
             if (cnt) {
                 r += cnt;
-                if (lane == 0) sts_u32(sm.ctrl + 4u, r);
+                if (lane == 0) sts_rel_u32(sm.ctrl + 4u, r);
             }
         }
         {
             // symbols [p, done) are decoded: mode symbols left no trace, the others a tagged result word
-            const uint32_t d = lds_u32(sm.ctrl + 8u);
+            const uint32_t d = lds_acq_u32(sm.ctrl + 8u);
             const int32_t avail = (int32_t)(d - p);
             const uint32_t cnt = avail <= 0 ? 0u : (avail > 32 ? 32u : (uint32_t)avail);
             if ((uint32_t)lane < cnt) {
@@ -1129,7 +1160,7 @@ __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm,
             __syncwarp();
             if (cnt) {
                 p += cnt;
-                if (lane == 0) sts_u32(sm.ctrl, p);
+                if (lane == 0) sts_rel_u32(sm.ctrl, p);
             }
         }
     }
@@ -1144,10 +1175,9 @@ __device__ __noinline__ void encode_grid(const SLoc &S, const SmemLayout &sm, co
     const uint32_t ring_mask = (uint32_t)S.ring - 1u;
     for (uint32_t j = ord_begin; j != ord_end; j++) {
         const uint32_t slot = j & ring_mask;
-        uint4 m;
-        do {
-            m = lds_v4(sm.meta + slot * 16u);
-        } while (!__all_sync(0xffffffffu, m.w == j + 1u));
+        while (!__all_sync(0xffffffffu, lds_acq_u32(sm.meta + slot * 16u + 12u) == j + 1u)) {
+        }
+        const uint4 m = lds_v4(sm.meta + slot * 16u);
         const uint32_t L0 = lds_u32(sm.win + slot * (CCD_WIN * 4) + (uint32_t)lane * 4u);
         const uint32_t L1 = __shfl_down_sync(0xffffffffu, L0, 1);  // lane 31 keeps L0: empty interval
         const int mu_idx = (int)(m.z & 0xffffu), sc_idx = (int)(m.z >> 16);
@@ -1187,7 +1217,7 @@ __device__ __noinline__ void encode_grid(const SLoc &S, const SmemLayout &sm, co
         if (lane == 0) {
             sts_u8(sm.rows + (m.y & 0xffffu), sym);
             S.latents[m.x] = (int8_t)sym;
-            sts_u32(sm.ctrl, j + 1u);
+            sts_rel_u32(sm.ctrl, j + 1u);
         }
         __syncwarp();
     }

@@ -240,3 +240,21 @@ def test_corrupt_headers_and_payloads_never_crash():
             assert e.code in (-1, -2, -4)
             outcomes["nn_error"] += 1
     assert sum(outcomes.values()) == 300 and outcomes["accepted"] > 0 and outcomes["parse_error"] + outcomes["rejected"] + outcomes["nn_error"] > 0
+
+
+def test_corrupt_coolchic_header_raises_value_error():
+    """impossible header values surface as ValueError (not ZeroDivisionError / IndexError)."""
+    import pytest
+
+    from coolchic_b200._desc import desc_from_header
+    from coolchic_b200.bitstream.header import CoolChicHeader, FrameHeader, VideoHeader
+
+    data = open(os.path.join(GOLDEN, "kodim14.cool"), "rb").read()
+    rest = FrameHeader().read_header(VideoHeader().read_header(data))
+    for key, bad in (("img_size", [0, 768]), ("n_layer_synthesis", 0), ("latent_resolution", [6, 0]),
+                     ("hyperlatent_resolution", [6, 4])):
+        c = CoolChicHeader()
+        c.read_header(rest)
+        c._values[key] = bad
+        with pytest.raises(ValueError):
+            desc_from_header(c)
