@@ -1054,11 +1054,14 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
         a3 = lds_v4(o + 48u);
         while (true) {
             // (K entries in a0..a3 valid for j; 2 K more must be ready for the two prefetches of this iteration)
-            if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) {
-                refresh();
-                if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) break;
+            // (the two rare maintenance cases behind ONE test: every skipped block is a taken branch for this warp)
+            if (((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) | (wpos - wbase >= 32u)) {
+                if (wpos - wbase >= 32u) advance_words();
+                if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) {
+                    refresh();
+                    if ((int32_t)(limit - j) < (int32_t)(CCD_STEADY_MIN * K)) break;
+                }
             }
-            if (wpos - wbase >= 32u) advance_words();
             o = sm.hot + ((j + K) & ring_mask) * 16u;
             b0 = lds_v4(o);
             b1 = lds_v4(o + 16u);
