@@ -759,10 +759,13 @@ __device__ __forceinline__ FastOut fast_step(uint64_t &D, uint64_t &R, uint32_t 
     const uint64_t P0 = scale * h.x, P1 = scale * h.y, P2 = scale * h.z, P3 = scale * h.w;
     const bool c1 = D >= P1, c2 = D >= P2;
     FastOut o;
-    o.far = (uint32_t)(D < P0) | (uint32_t)(D >= P3);
     const uint64_t nlo = c2 ? P2 : (c1 ? P1 : P0);
     const uint64_t nhi = c2 ? P3 : (c1 ? P2 : P1);
     const uint64_t Dn = D - nlo, Rn = nhi - nlo;
+    // none of the three candidates <=> Dn >= Rn: D < P0 wraps Dn above any Rn (Rn <= R < 2^64 - (P0 - D) would need
+    // 2^64 + D < P1), D >= P3 leaves Dn >= P3 - P2 = Rn; an empty candidate interval (left(M-1) == left(M) at the
+    // lower end of the alphabet) wraps as well
+    o.far = (uint32_t)(Dn >= Rn);
     const bool renorm = (uint32_t)(Rn >> 32) == 0u;
     D = renorm ? ((Dn << 32) | w0) : Dn;
     R = renorm ? (Rn << 32) : Rn;

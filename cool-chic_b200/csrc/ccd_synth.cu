@@ -882,6 +882,487 @@ __global__ void __launch_bounds__(SF_THREADS) k_tail_syn(const TailSynJob *__res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_tail_syn2: same contract as k_tail_syn, restructured for instruction efficiency (k_tail_syn issues ~3 650
+// instructions per pixel for 862 FMAs):
+//   * the halo of the stage-A region is rounded up to an even number of pixels, so that the region starts on even
+//     frame coordinates and stage A works on 2 x 2 QUADS with compile-time parities: the 8x8 stride-2 transposed
+//     conv reads ONE 5 x 5 window per channel for its four outputs, its taps come as 16 vector loads (re-laid
+//     [du][t1][dv][t2]); the 7x7 pre-concatenation conv slides over 8 rows of 8 values (converted to fp32 once per
+//     tile); the two 1x1 layers share every weight fetch between the four positions;
+//   * out-of-frame positions of the region (replicate padding of the 3x3 layers) are copies of the clamped
+//     position's values (the 1x1 layers are pointwise), filled by a fix-up pass on border tiles only;
+//   * the 3x3 layers evaluate two horizontally adjacent outputs per thread from one 3 x 4 window per channel, their
+//     weights re-laid [ci][ky][kx][co] (one vector load per tap); stores are 64-bit.
+// Every output keeps its canonical accumulation order: bit-identical to k_tail_syn, k_syn_fused and the oracle.
+__host__ __device__ inline int ts2_n3e(int n3) { return (n3 + 1) & ~1; }
+constexpr int TS2_THREADS = 192;  // 180 quads per 32 x 16 tile with a 2-pixel halo; three CTAs per SM
+
+template <int CINP, int C>
+__global__ void __launch_bounds__(TS2_THREADS, 3) k_tail_syn2(const TailSynJob *__restrict__ jobs) {
+    extern __shared__ __align__(128) unsigned char ts_raw[];
+    const TailSynJob &P = jobs[blockIdx.z];
+    const int H = P.h, W = P.w;
+    const int x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
+    if (x0 >= W || y0 >= H) return;
+    const int n3 = P.n3, n3e = ts2_n3e(n3), hid = P.hid, cin = P.cin, cc = cin - 1;
+    const int RW = SF_TW + 2 * n3e, RH = SF_TH + 2 * n3e;
+    const int LW = ts_lw(n3e), LH = ts_lh(n3e), SW = ts_sw(n3e), SH = ts_sh(n3e);
+    constexpr int CP = (C + 3) & ~3;  // output channels padded to a multiple of 4 (vector loads of weights)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(ts_raw);
+    int8_t *Lt = reinterpret_cast<int8_t *>(ts_raw + 128);                          // [LH][LW] int8 (TMA destination)
+    float *St = reinterpret_cast<float *>(ts_raw + 128 + ((LW * LH + 127) & ~127)); // [cc][SH][SW]
+    float *Lf = St + ((cc * SH * SW + 31) & ~31);  // [LH][LW] the latent tile as fp32
+    float *sw0 = Lf + LW * LH;               // [hid][CINP]
+    float *sb0 = sw0 + hid * CINP;
+    float *sw1 = sb0 + ((hid + 3) & ~3);     // [hid][CP]
+    float *sb1 = sw1 + hid * CP;
+    float *sw3 = sb1 + CP;                   // [2][C][3][3][CP]
+    float *sb3 = sw3 + 2 * C * 9 * CP;
+    float *sws = sb3 + 2 * CP;               // [C][CINP]
+    float *sbs = sws + C * CINP;
+    float *swo = sbs + CP;                   // [C][CP]
+    float *sbo = swo + C * CP;
+    float *skt = sbo + CP;                   // [2 du][4 t1][2 dv][4 t2]
+    float *skc = skt + 64;                   // [7][8] (rows padded)
+    float *bufA = skc + 56;                  // [C][RH][RW]
+    float *bufB = bufA + C * RH * RW;        // [C][RH-2][RW-2]   (n3 == 2)
+    float *sstab = bufB + (n3 == 2 ? C * (RH - 2) * (RW - 2) : 0);  // [C][SF_TH][SF_TW]
+    const int tid = threadIdx.x;
+    const int Y0 = y0 - n3e, X0 = x0 - n3e;                 // stage-A region origin (even frame coordinates)
+    const int ly0 = Y0 - 3, lx0 = (X0 - 3) & ~15;           // latent tile (16-byte aligned start)
+    const int sy0 = ((Y0 < 0 ? 0 : Y0) >> 1) - 2, sx0 = (((X0 < 0 ? 0 : X0) >> 1) - 2) & ~3;  // stack tile
+    const int ch = P.ch, cw = P.cw;
+    // ---- stage 0: tiles -> shared memory
+    if (P.use_tma) {
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(LW * LH + cc * SH * SW * 4);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            const uint64_t tm0 = reinterpret_cast<uint64_t>(P.tmap_lat), tm1 = reinterpret_cast<uint64_t>(P.tmap_stk);
+            if (P.use_tma & 2) {
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm0) : "memory");
+                asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tm1) : "memory");
+            }
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                ::"r"((uint32_t)__cvta_generic_to_shared(Lt)), "l"(tm0), "r"(lx0), "r"(ly0), "r"(bar_a)
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"((uint32_t)__cvta_generic_to_shared(St)), "l"(tm1), "r"(sx0), "r"(sy0), "r"(0), "r"(bar_a)
+                : "memory");
+        }
+    } else {
+        for (int i = tid; i < LW * LH; i += TS2_THREADS) {
+            const int r = i / LW, c = i - r * LW;
+            const int gy = ly0 + r, gx = lx0 + c;
+            Lf[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? (float)P.lat[(size_t)gy * W + gx] : 0.0f;
+        }
+        for (int i = tid; i < cc * SH * SW; i += TS2_THREADS) {
+            const int c = i / (SH * SW), rem = i - c * SH * SW, r = rem / SW, col = rem - r * SW;
+            const int gy = sy0 + r, gx = sx0 + col;
+            float v = 0.0f;
+            if (gy >= 0 && gy < ch && gx >= 0 && gx < cw)
+                v = P.stk8 ? (float)P.stk8[((size_t)c * ch + gy) * cw + gx] : __ldg(P.stk + ((size_t)c * ch + gy) * cw + gx);
+            St[i] = v;
+        }
+    }
+    // ---- weights (overlaps the bulk copies)
+    for (int i = tid; i < hid * CINP; i += TS2_THREADS) {
+        const int hh = i / CINP, ci = i - hh * CINP;
+        sw0[i] = ci < cin ? P.w0[hh * cin + ci] : 0.0f;
+    }
+    for (int i = tid; i < hid; i += TS2_THREADS) sb0[i] = P.b0[i];
+    for (int i = tid; i < hid * CP; i += TS2_THREADS) {
+        const int hh = i / CP, c = i - hh * CP;
+        sw1[i] = c < C ? P.w1[c * hid + hh] : 0.0f;
+    }
+    for (int i = tid; i < CP; i += TS2_THREADS) {
+        sb1[i] = i < C ? P.b1[i] : 0.0f;
+        sbs[i] = (i < C && P.stab_in) ? P.bs[i] : 0.0f;
+        sbo[i] = i < C ? P.bo[i] : 0.0f;
+        for (int l = 0; l < 2; l++) sb3[l * CP + i] = (i < C && l < n3) ? P.b3[l][i] : 0.0f;
+    }
+    for (int l = 0; l < n3; l++)
+        for (int i = tid; i < C * 9 * CP; i += TS2_THREADS) {
+            const int co = i % CP, t = i / CP;  // t = ci * 9 + ky * 3 + kx
+            sw3[l * C * 9 * CP + i] = co < C ? P.w3[l][(co * C + t / 9) * 9 + t % 9] : 0.0f;
+        }
+    for (int i = tid; i < C * CINP; i += TS2_THREADS) {
+        const int c = i / CINP, ci = i - c * CINP;
+        sws[i] = (ci < P.stab_in) ? P.ws[c * P.stab_in + ci] : 0.0f;
+    }
+    for (int i = tid; i < C * CP; i += TS2_THREADS) {
+        const int c = i / CP, k = i - c * CP;
+        swo[i] = k < C ? P.wo[c * C + k] : 0.0f;
+    }
+    for (int i = tid; i < 64; i += TS2_THREADS) {
+        const int t2 = i & 3, dv = (i >> 2) & 1, t1 = (i >> 3) & 3, du = i >> 5;
+        skt[i] = P.kt[(1 - du) + 6 - 2 * t1][(1 - dv) + 6 - 2 * t2];
+    }
+    for (int i = tid; i < 56; i += TS2_THREADS) skc[i] = (i & 7) < 7 ? P.kc[i >> 3][i & 7] : 0.0f;
+    if (P.use_tma) {
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar_a)
+                : "memory");
+        }
+        for (int i = tid; i < LW * LH; i += TS2_THREADS) Lf[i] = (float)Lt[i];
+    }
+    __syncthreads();
+
+    // ---- stage A on 2 x 2 quads of the region
+    const int QW = RW / 2, nQ = (RH / 2) * QW;
+    for (int q = tid; q < nQ; q += TS2_THREADS) {
+        const int qy = q / QW, qx = q - qy * QW;
+        const int u0 = Y0 + 2 * qy, v0 = X0 + 2 * qx;  // even
+        bool in[4];
+        bool any_in = false;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const int u = u0 + (p >> 1), v = v0 + (p & 1);
+            in[p] = u >= 0 && u < H && v >= 0 && v < W;
+            any_in |= in[p];
+        }
+        if (!any_in) continue;  // (filled by the fix-up pass)
+        float x[4][CINP];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int ci = 0; ci < CINP; ci++) x[p][ci] = 0.0f;
+        {
+            // channel 0: conv2d(latent, kron 7x7, zero padding) + latent (upsampling.py:189-196), sliding over the 8 rows
+            // of the quad's 8 x 8 window; every output accumulates in (ka, kb) raster order
+            const float *lp = Lf + (u0 - 3 - ly0) * LW + (v0 - 3 - lx0);
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, centre[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            float wprev[7];
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                float r[8];
+#pragma unroll
+                for (int b = 0; b < 8; b++) r[b] = lp[a * LW + b];
+                float wcur[7];
+                if (a < 7) {
+#pragma unroll
+                    for (int b = 0; b < 7; b++) wcur[b] = skc[a * 8 + b];
+                }
+#pragma unroll
+                for (int b = 0; b < 7; b++) {
+                    if (a < 7) {  // row a is tap row ka = a of the outputs with dy = 0
+                        acc[0] = __fmaf_rn(wcur[b], r[b], acc[0]);
+                        acc[1] = __fmaf_rn(wcur[b], r[b + 1], acc[1]);
+                    }
+                    if (a >= 1) {  // and tap row ka = a - 1 of the outputs with dy = 1
+                        acc[2] = __fmaf_rn(wprev[b], r[b], acc[2]);
+                        acc[3] = __fmaf_rn(wprev[b], r[b + 1], acc[3]);
+                    }
+                }
+                if (a == 3) { centre[0] = r[3]; centre[1] = r[4]; }
+                if (a == 4) { centre[2] = r[3]; centre[3] = r[4]; }
+                if (a < 7) {
+#pragma unroll
+                    for (int b = 0; b < 7; b++) wprev[b] = wcur[b];
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 4; p++) x[p][0] = __fadd_rn(acc[p], centre[p]);
+        }
+        {
+            // channels 1 .. cc: transposed conv (8x8 kron, stride 2, replicate-padded input, crop 11; upsampling.py:312-325)
+            const int qy0 = u0 >> 1, qx0 = v0 >> 1;  // (arithmetic shifts: u0, v0 may be negative on border tiles)
+            int ro[5], co[5];
+#pragma unroll
+            for (int t = 0; t < 5; t++) {
+                ro[t] = (clampi(qy0 - 2 + t, 0, ch - 1) - sy0) * SW;
+                co[t] = clampi(qx0 - 2 + t, 0, cw - 1) - sx0;
+            }
+#pragma unroll
+            for (int c = 0; c < CINP - 1; c++) {
+                if (c < cc) {
+                    const float *sp = St + c * SH * SW;
+                    float win[5][5];
+#pragma unroll
+                    for (int i = 0; i < 5; i++)
+#pragma unroll
+                        for (int j = 0; j < 5; j++) win[i][j] = sp[ro[i] + co[j]];
+#pragma unroll
+                    for (int du = 0; du < 2; du++)
+#pragma unroll
+                        for (int dv = 0; dv < 2; dv++) {
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int t1 = 0; t1 < 4; t1++) {
+                                const float4 w4 = *reinterpret_cast<const float4 *>(skt + ((du * 4 + t1) * 2 + dv) * 4);
+                                acc = __fmaf_rn(w4.x, win[t1 + du][0 + dv], acc);
+                                acc = __fmaf_rn(w4.y, win[t1 + du][1 + dv], acc);
+                                acc = __fmaf_rn(w4.z, win[t1 + du][2 + dv], acc);
+                                acc = __fmaf_rn(w4.w, win[t1 + du][3 + dv], acc);
+                            }
+                            x[du * 2 + dv][c + 1] = acc;
+                        }
+                }
+            }
+        }
+        float o[4][C];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int c = 0; c < C; c++) o[p][c] = sb1[c];
+        for (int hh = 0; hh < hid; hh++) {
+            float wv[CINP];
+#pragma unroll
+            for (int v = 0; v < CINP / 4; v++) {
+                const float4 t = *reinterpret_cast<const float4 *>(sw0 + hh * CINP + 4 * v);
+                wv[4 * v] = t.x; wv[4 * v + 1] = t.y; wv[4 * v + 2] = t.z; wv[4 * v + 3] = t.w;
+            }
+            float w1v[CP];
+#pragma unroll
+            for (int v = 0; v < CP / 4; v++) {
+                const float4 t = *reinterpret_cast<const float4 *>(sw1 + hh * CP + 4 * v);
+                w1v[4 * v] = t.x; w1v[4 * v + 1] = t.y; w1v[4 * v + 2] = t.z; w1v[4 * v + 3] = t.w;
+            }
+            const float bb = sb0[hh];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                float a = bb;
+#pragma unroll
+                for (int ci = 0; ci < CINP; ci++)
+                    if (ci < cin) a = __fmaf_rn(wv[ci], x[p][ci], a);
+                if (P.relu0) a = fmaxf(a, 0.0f);
+#pragma unroll
+                for (int c = 0; c < C; c++) o[p][c] = __fmaf_rn(w1v[c], a, o[p][c]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            if (!in[p]) continue;
+            const int py = 2 * qy + (p >> 1), px = 2 * qx + (p & 1);
+#pragma unroll
+            for (int c = 0; c < C; c++) bufA[(c * RH + py) * RW + px] = P.relu1 ? fmaxf(o[p][c], 0.0f) : o[p][c];
+            const int ty = py - n3e, tx = px - n3e;
+            if (P.stab_in && ty >= 0 && ty < SF_TH && tx >= 0 && tx < SF_TW) {
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float a = sbs[c];
+#pragma unroll
+                    for (int ci = 0; ci < CINP; ci++)
+                        if (ci < P.stab_in) a = __fmaf_rn(sws[c * CINP + ci], x[p][ci], a);
+                    sstab[(c * SF_TH + ty) * SF_TW + tx] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- replicate padding on border tiles: out-of-frame positions of the region copy the clamped position
+    if (Y0 < 0 || X0 < 0 || Y0 + RH > H || X0 + RW > W) {
+        for (int pp = tid; pp < RH * RW; pp += TS2_THREADS) {
+            const int py = pp / RW, px = pp - py * RW;
+            const int u = Y0 + py, v = X0 + px;
+            if (u >= 0 && u < H && v >= 0 && v < W) continue;
+            const int sy = clampi(u, 0, H - 1) - Y0, sx = clampi(v, 0, W - 1) - X0;
+#pragma unroll
+            for (int c = 0; c < C; c++) bufA[(c * RH + py) * RW + px] = bufA[(c * RH + sy) * RW + sx];
+        }
+        __syncthreads();
+    }
+    // ---- 3x3 layers: two horizontally adjacent outputs per thread
+    const float *cur = bufA;
+    int cwid = RW, chh = RH, off = n3e;
+    for (int l = 0; l < n3 - 1; l++) {
+        const int ow = cwid - 2, oh = chh - 2;
+        const float *wl = sw3 + l * C * 9 * CP;
+        for (int pp = tid; pp < (ow / 2) * oh; pp += TS2_THREADS) {
+            const int py = pp / (ow / 2), px = 2 * (pp - py * (ow / 2));
+            const int gy = clampi(y0 - (off - 1) + py, 0, H - 1);
+            const int by = gy - (y0 - off);
+            const int bx0 = clampi(x0 - (off - 1) + px, 0, W - 1) - (x0 - off);
+            const int bx1 = clampi(x0 - (off - 1) + px + 1, 0, W - 1) - (x0 - off);
+            float acc0[C], acc1[C];
+#pragma unroll
+            for (int co = 0; co < C; co++) acc0[co] = acc1[co] = sb3[l * CP + co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++)
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++) {
+                    const float *row = cur + (ci * chh + by + ky - 1) * cwid;
+                    float v0[3], v1[3];
+                    if (bx1 == bx0 + 1) {
+                        v0[0] = row[bx0 - 1]; v0[1] = row[bx0]; v0[2] = row[bx0 + 1];
+                        v1[0] = v0[1]; v1[1] = v0[2]; v1[2] = row[bx0 + 2];
+                    } else {
+                        v0[0] = row[bx0 - 1]; v0[1] = row[bx0]; v0[2] = row[bx0 + 1];
+                        v1[0] = row[bx1 - 1]; v1[1] = row[bx1]; v1[2] = row[bx1 + 1];
+                    }
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        float w[CP];
+#pragma unroll
+                        for (int v = 0; v < CP / 4; v++) {
+                            const float4 t = *reinterpret_cast<const float4 *>(wl + ((ci * 3 + ky) * 3 + kx) * CP + 4 * v);
+                            w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+                        }
+#pragma unroll
+                        for (int co = 0; co < C; co++) {
+                            acc0[co] = __fmaf_rn(w[co], v0[kx], acc0[co]);
+                            acc1[co] = __fmaf_rn(w[co], v1[kx], acc1[co]);
+                        }
+                    }
+                }
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                float a0 = acc0[co], a1 = acc1[co];
+                if (P.res3[l]) {
+                    a0 = __fadd_rn(a0, cur[(co * chh + by) * cwid + bx0]);
+                    a1 = __fadd_rn(a1, cur[(co * chh + by) * cwid + bx1]);
+                }
+                if (P.relu3[l]) { a0 = fmaxf(a0, 0.0f); a1 = fmaxf(a1, 0.0f); }
+                bufB[(co * oh + py) * ow + px] = a0;
+                bufB[(co * oh + py) * ow + px + 1] = a1;
+            }
+        }
+        __syncthreads();
+        cur = bufB;
+        cwid = ow;
+        chh = oh;
+        off -= 1;
+    }
+    // ---- last stage on the tile (one pair of pixels per thread): last 3x3 layer (if any), + stabiliser, output
+    // transform, frame tail, 64-bit stores
+    const float M = P.M;
+    float *uvq = sstab;  // 4:2:0 tail: rounded U, V of the tile where the stabiliser output was (own position, read first)
+    for (int pp = tid; pp < (SF_TW / 2) * SF_TH; pp += TS2_THREADS) {
+        const int ty = pp / (SF_TW / 2), tx = 2 * (pp - ty * (SF_TW / 2));
+        const int gy = y0 + ty, gx = x0 + tx;
+        const bool in0 = gy < H && gx < W, in1 = gy < H && gx + 1 < W;
+        const int tyc = in0 ? ty : 0, txc = in0 ? tx : 0;  // (out-of-frame pairs compute on a valid position, store nothing)
+        const int by = tyc + off, bx0 = txc + off;
+        const int bx1 = (in1 ? txc + 1 : txc) + off;
+        float t0[C], t1[C];
+        if (n3 > 0) {
+            const int l = n3 - 1;
+            const float *wl = sw3 + l * C * 9 * CP;
+#pragma unroll
+            for (int co = 0; co < C; co++) t0[co] = t1[co] = sb3[l * CP + co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++)
+#pragma unroll
+                for (int ky = 0; ky < 3; ky++) {
+                    const float *row = cur + (ci * chh + by + ky - 1) * cwid;
+                    float v0[3], v1[3];
+                    v0[0] = row[bx0 - 1]; v0[1] = row[bx0]; v0[2] = row[bx0 + 1];
+                    if (bx1 == bx0 + 1) {
+                        v1[0] = v0[1]; v1[1] = v0[2]; v1[2] = row[bx0 + 2];
+                    } else {
+                        v1[0] = row[bx1 - 1]; v1[1] = row[bx1]; v1[2] = row[bx1 + 1];
+                    }
+#pragma unroll
+                    for (int kx = 0; kx < 3; kx++) {
+                        float w[CP];
+#pragma unroll
+                        for (int v = 0; v < CP / 4; v++) {
+                            const float4 t = *reinterpret_cast<const float4 *>(wl + ((ci * 3 + ky) * 3 + kx) * CP + 4 * v);
+                            w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+                        }
+#pragma unroll
+                        for (int co = 0; co < C; co++) {
+                            t0[co] = __fmaf_rn(w[co], v0[kx], t0[co]);
+                            t1[co] = __fmaf_rn(w[co], v1[kx], t1[co]);
+                        }
+                    }
+                }
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                if (P.res3[l]) {
+                    t0[co] = __fadd_rn(t0[co], cur[(co * chh + by) * cwid + bx0]);
+                    t1[co] = __fadd_rn(t1[co], cur[(co * chh + by) * cwid + bx1]);
+                }
+                if (P.relu3[l]) { t0[co] = fmaxf(t0[co], 0.0f); t1[co] = fmaxf(t1[co], 0.0f); }
+            }
+        } else {
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                t0[co] = cur[(co * chh + by) * cwid + bx0];
+                t1[co] = cur[(co * chh + by) * cwid + bx1];
+            }
+        }
+        if (P.stab_in) {
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                t0[co] = __fadd_rn(t0[co], sstab[(co * SF_TH + tyc) * SF_TW + txc]);
+                t1[co] = __fadd_rn(t1[co], sstab[(co * SF_TH + tyc) * SF_TW + (in1 ? txc + 1 : txc)]);
+            }
+        }
+        float ov0[C], ov1[C];
+#pragma unroll
+        for (int co = 0; co < C; co++) {
+            float a0 = sbo[co], a1 = sbo[co];
+#pragma unroll
+            for (int ci = 0; ci < C; ci++) {
+                a0 = __fmaf_rn(swo[co * CP + ci], t0[ci], a0);
+                a1 = __fmaf_rn(swo[co * CP + ci], t1[ci], a1);
+            }
+            ov0[co] = a0;
+            ov1[co] = a1;
+        }
+        const size_t oi = (size_t)gy * W + gx;
+        if (P.finish != 0) {
+#pragma unroll
+            for (int co = 0; co < C; co++) {
+                ov0[co] = quant(ov0[co], M);
+                ov1[co] = quant(ov1[co], M);
+            }
+        }
+        const int n_full = P.finish == 2 ? 1 : C;  // planes stored at full resolution by this loop
+#pragma unroll
+        for (int co = 0; co < C; co++) {
+            if (co < n_full) {
+                float a0 = ov0[co], a1 = ov1[co];
+                if (P.finish != 0) { a0 = quant(clamp01(a0), M); a1 = quant(clamp01(a1), M); }
+                float *dst = P.out[co] + oi;
+                if (in1 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) *reinterpret_cast<float2 *>(dst) = make_float2(a0, a1);
+                else {
+                    if (in0) P.out[co][oi] = a0;
+                    if (in1) P.out[co][oi + 1] = a1;
+                }
+            }
+        }
+        if (P.finish == 2) {
+            // (rounded U, V of own positions; read above, overwritten now)
+            uvq[(0 * SF_TH + ty) * SF_TW + tx] = ov0[1 < C ? 1 : 0];
+            uvq[(0 * SF_TH + ty) * SF_TW + tx + 1] = ov1[1 < C ? 1 : 0];
+            uvq[(1 * SF_TH + ty) * SF_TW + tx] = ov0[2 < C ? 2 : 0];
+            uvq[(1 * SF_TH + ty) * SF_TW + tx + 1] = ov1[2 < C ? 2 : 0];
+        }
+    }
+    if (P.finish == 2) {
+        __syncthreads();
+        const int h2 = H / 2, w2 = W / 2;
+        for (int pp = tid; pp < 2 * (SF_TW / 2) * (SF_TH / 2); pp += TS2_THREADS) {
+            const int c = pp / ((SF_TW / 2) * (SF_TH / 2)), r = pp - c * (SF_TW / 2) * (SF_TH / 2);
+            const int by = r / (SF_TW / 2), bx = r - by * (SF_TW / 2);
+            const int y2 = y0 / 2 + by, x2 = x0 / 2 + bx;
+            if (y2 >= h2 || x2 >= w2) continue;
+            const float *q = uvq + (c * SF_TH + 2 * by) * SF_TW + 2 * bx;
+            float s = 0.0f;
+            s = __fadd_rn(s, q[0]);
+            s = __fadd_rn(s, q[1]);
+            s = __fadd_rn(s, q[SF_TW]);
+            s = __fadd_rn(s, q[SF_TW + 1]);
+            P.out[1 + c][(size_t)y2 * w2 + x2] = quant(clamp01(__fdiv_rn(s, 4.0f)), M);
+        }
+    }
+}
+
 __global__ void k_add(float *__restrict__ a, const float *__restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = __fadd_rn(a[i], b[i]);
@@ -1179,6 +1660,16 @@ PFN_encodeTiled get_encode_tiled() {
 }
 }  // namespace
 
+// development switch: CCD_TAIL_V=1 selects the first version of the fused tail kernel (k_tail_syn), default k_tail_syn2
+static int tail_version() {
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("CCD_TAIL_V");
+        v = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    return v;
+}
+
 // Fills one TailSynJob (host memory).  Returns 1 when the tiles are staged with TMA, 0 when with plain loads
 // (pitches / addresses that cuTensorMapEncodeTiled does not take), < 0 when the architecture is outside the family.
 int ccd_tail_fill_syn(void *dst, const CcdTailSynDesc &T) {
@@ -1229,11 +1720,12 @@ int ccd_tail_fill_syn(void *dst, const CcdTailSynDesc &T) {
         (reinterpret_cast<uintptr_t>(T.stk) % 16) == 0) {
         const uint64_t gd0[2] = {(uint64_t)T.w, (uint64_t)T.h};
         const uint64_t gs0[1] = {(uint64_t)T.w};
-        const uint32_t bx0[2] = {(uint32_t)ts_lw(J.n3), (uint32_t)ts_lh(J.n3)};
+        const int n3t = tail_version() == 2 ? ts2_n3e(J.n3) : J.n3;  // halo of the staged tiles
+        const uint32_t bx0[2] = {(uint32_t)ts_lw(n3t), (uint32_t)ts_lh(n3t)};
         const uint32_t es[3] = {1, 1, 1};
         const uint64_t gd1[3] = {(uint64_t)T.cw, (uint64_t)T.ch, (uint64_t)cc};
         const uint64_t gs1[2] = {(uint64_t)T.cw * 4, (uint64_t)T.cw * 4 * (uint64_t)T.ch};
-        const uint32_t bx1[3] = {(uint32_t)ts_sw(J.n3), (uint32_t)ts_sh(J.n3), (uint32_t)cc};
+        const uint32_t bx1[3] = {(uint32_t)ts_sw(n3t), (uint32_t)ts_sh(n3t), (uint32_t)cc};
         const int r0 = enc(J.tmap_lat, 0, 2, const_cast<int8_t *>(T.lat), gd0, gs0, bx0, es, 0, 0, 1, 0);
         const int r1 = enc(J.tmap_stk, 7, 3, const_cast<float *>(T.stk), gd1, gs1, bx1, es, 0, 0, 1, 0);
         J.use_tma = (r0 == 0 && r1 == 0) ? 3 : 0;  // bit 0: TMA staging, bit 1: descriptor fence before the first use
@@ -1249,19 +1741,26 @@ int ccd_tail_fill_syn(void *dst, const CcdTailSynDesc &T) {
 template <int CINP, int C>
 static int launch_tail_syn(const void *d_jobs, int n_jobs, int n3_max, int hid_max, int max_w, int max_h, cudaStream_t st) {
     constexpr int CP = (C + 3) & ~3;
-    const int RW = SF_TW + 2 * n3_max, RH = SF_TH + 2 * n3_max;
-    size_t bytes = 128 + (((size_t)ts_lw(n3_max) * ts_lh(n3_max) + 127) & ~(size_t)127);
-    size_t fl = (((size_t)(CINP - 1) * ts_sh(n3_max) * ts_sw(n3_max) + 31) & ~(size_t)31);
-    fl += (size_t)hid_max * CINP + hid_max + (size_t)hid_max * CP + CP + 2 * C * C * 9 + 2 * CP + C * CINP + CP + C * CP + CP + 64 + 52;
+    const bool v2 = tail_version() == 2;
+    const int n3t = v2 ? ts2_n3e(n3_max) : n3_max;
+    const int RW = SF_TW + 2 * n3t, RH = SF_TH + 2 * n3t;
+    size_t bytes = 128 + (((size_t)ts_lw(n3t) * ts_lh(n3t) + 127) & ~(size_t)127);
+    size_t fl = (((size_t)(CINP - 1) * ts_sh(n3t) * ts_sw(n3t) + 31) & ~(size_t)31);
+    if (v2) {
+        fl += (size_t)ts_lw(n3t) * ts_lh(n3t);
+        fl += (size_t)hid_max * CINP + ((hid_max + 3) & ~3) + (size_t)hid_max * CP + CP + 2 * C * 9 * CP + 2 * CP + C * CINP + CP + C * CP + CP + 64 + 56;
+    } else {
+        fl += (size_t)hid_max * CINP + hid_max + (size_t)hid_max * CP + CP + 2 * C * C * 9 + 2 * CP + C * CINP + CP + C * CP + CP + 64 + 52;
+    }
     fl += (size_t)C * RH * RW + (n3_max == 2 ? (size_t)C * (RH - 2) * (RW - 2) : 0) + (size_t)C * SF_TH * SF_TW;
     const size_t smem = bytes + fl * sizeof(float);
-    auto kern = k_tail_syn<CINP, C>;
+    auto kern = v2 ? k_tail_syn2<CINP, C> : k_tail_syn<CINP, C>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     const dim3 grid((max_w + SF_TW - 1) / SF_TW, (max_h + SF_TH - 1) / SF_TH, (unsigned)n_jobs);
-    kern<<<grid, SF_THREADS, smem, st>>>(reinterpret_cast<const TailSynJob *>(d_jobs));
+    kern<<<grid, v2 ? TS2_THREADS : SF_THREADS, smem, st>>>(reinterpret_cast<const TailSynJob *>(d_jobs));
     g_ccd_launches++;
     return (int)cudaGetLastError();
 }

@@ -645,3 +645,43 @@ def test_corrupt_streams_fail_cleanly_on_the_device(ctx, seed_stream):
             n_err += 1
     assert n_ok + n_err == 24
     assert torch.equal(ctx.decode_coolchic(d, nnb, lb), good)  # the context is still healthy
+
+
+def test_integration_stub_b_runs_against_the_reference_header(ctx, kodim14):
+    """INTEGRATION.md, stub B, executed as documented: the code block is taken from the file, pointed at the in-tree
+    library, and driven with the REFERENCE's own VideoHeader / FrameHeader / CoolChicHeader objects (staged copy
+    oracle/_ref or /root/reference): its output equals this package's decode of the same Cool-chic."""
+    import re
+    import sys
+    import types
+    import warnings
+
+    import torch
+
+    ref_root = next((p for p in (os.path.join(ROOT, "oracle", "_ref"), "/root/reference")
+                     if os.path.isdir(os.path.join(p, "coolchic"))), None)
+    if ref_root is None:
+        pytest.skip("the reference package is not staged (oracle/make_ref.sh)")
+    for p in (ref_root, os.path.join(ROOT, "oracle", "refshim")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from coolchic.bitstream.header.header import CoolChicHeader as RefCC
+        from coolchic.bitstream.header.header import FrameHeader as RefFrame
+        from coolchic.bitstream.header.header import VideoHeader as RefVideo
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# coolchic/bitstream/component/coolchic_b200_stub\.py.*?)```", text, re.S).group(1)
+    code = code.replace('"/path/to/cool-chic_b200/csrc/libccdec.so"', repr(os.path.join(ROOT, "cool-chic_b200", "csrc", "libccdec.so")))
+    stub = types.ModuleType("coolchic_b200_stub")
+    exec(compile(code, "INTEGRATION.md:stub_b", "exec"), stub.__dict__)
+    rest = RefVideo().read_header(kodim14["data"])
+    rest = RefFrame().read_header(rest)
+    cc = RefCC()
+    rest = cc.read_header(rest)
+    n_nn, n_lat = cc.get_value("nn_n_bytes"), cc.get_value("n_bytes_latent")
+    out, none = stub.encode_decode_coolchic(cc, rest[:n_nn], "decode", rest[n_nn:n_nn + n_lat])
+    torch.cuda.synchronize()
+    assert none is None
+    want = ctx.decode_coolchic(kodim14["desc"], kodim14["nn_bytes"], kodim14["lat_bytes"])
+    assert torch.equal(out, want)
