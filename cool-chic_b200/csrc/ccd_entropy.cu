@@ -218,7 +218,7 @@ __device__ __forceinline__ SmemLayout carve(unsigned char *base, int ring, int r
     L.hot = base_a + (uint32_t)p;
     p += (size_t)(ring + CCD_HOT_MIRROR) * 16;  // entries 0..7 are mirrored after the end: +32 B never wraps
     L.res = base_a + (uint32_t)p;
-    p += (size_t)ring * 4;
+    p += (size_t)(ring + 4) * 4;  // (+ CCD_RES_MIRROR slots)
     L.rows = base_a + (uint32_t)p;
     (void)rows;
     return L;
@@ -730,10 +730,14 @@ __device__ __forceinline__ uint32_t word_at(uint32_t wcur, uint32_t wnxt, uint32
     return __shfl_sync(0xffffffffu, (idx & 32u) ? wnxt : wcur, (int)idx);
 }
 
-// Result word of a symbol j that is NOT the mode (coder -> helper): [31] the value is the symbol itself (else the
-// window index t), [30] valid (an all-zero word never matches), [29:8] tag = (j + 1) mod 2^22, [7:0] value.
-// Mode symbols leave no trace: the helper infers them from `done` and the absence of a tagged word.
-__device__ __forceinline__ uint32_t res_tag(uint32_t j) { return 0x40000000u | (((j + 1u) & 0x3fffffu) << 8); }
+// Result word of a symbol j that is NOT the mode (coder -> helper): [31:10] tag = (j + 1) mod 2^22, [9] valid (an
+// all-zero word never matches), [8] the value is the symbol itself (else the window index t), [7:0] value.  The word of
+// symbol j + i is (j << 10) + a constant: one instruction in the coder.  The ring has CCD_RES_MIRROR slots behind its
+// end: the coder writes the words of consecutive symbols at consecutive addresses (no wrap test), the helper looks
+// at both places for the first slots of the ring.  Mode symbols leave no trace: the helper infers them from `done`
+// and the absence of a tagged word.
+#define CCD_RES_MIRROR 4u
+__device__ __forceinline__ uint32_t res_tag(uint32_t j) { return ((j + 1u) << 10) | 0x200u; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // The recursion, two tiers (cycle figures: tools/ubench/steps.cu on a B200, one warp):
@@ -807,7 +811,7 @@ __device__ __noinline__ FarOut coder_far(uint32_t wrow, uint32_t meta_slot, cons
     const uint4 r = slow_search((uint32_t)q, (int)(m.z & 0xffffu), (int)(m.z >> 16), scale_tab, lane);
     o.lo = scale * (uint64_t)__shfl_sync(0xffffffffu, r.x, (int)r.z);
     o.hi = scale * (uint64_t)__shfl_sync(0xffffffffu, r.y, (int)r.z);
-    o.rw = 0x80000000u | (r.w & 0xffu);
+    o.rw = 0x100u | (r.w & 0xffu);
     return o;
 }
 
@@ -1125,6 +1129,350 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     c.wbase = wbase;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SPECULATIVE coder (default): the lanes of the coder warp enumerate SYMBOL SEQUENCES.
+//   Lane l = c1 + 3 c2 + 9 c3 (27 lanes) assumes that the next three symbols are M1-1+c1, M2-1+c2, M3-1+c3 (Mi = the
+//   most probable symbol of symbol i) and runs the exact recursion -- interval test, update, renormalisation by
+//   selects -- on its OWN copy of (D, R): no branch, no vote, no shuffle inside the three steps (a vote / shuffle /
+//   shared-memory round trip costs this warp 27-35 cycles, which is why one round trip per SYMBOL loses against the
+//   scalar chain).  The candidate intervals of a symbol are disjoint, so at most one lane passes all three tests:
+//   it writes the result words of its non-mode symbols and its state into a 24-byte record; every lane reads the
+//   record back (ONE shared-memory round trip per three symbols).  A record without this round's tag means that one
+//   of the three symbols is outside {M-1, M, M+1} (0.8 ... 3 % of the symbols of a natural image): the prefix
+//   records tell how many symbols were decided, the next one goes through tier 2 / the window search.
+//   The words a renormalisation shifts in are uniform: W0, W1, W2 = word[wpos ...], a lane that has renormalised k
+//   times so far takes W_k (selects).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts_v4_if(uint32_t pred, uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.volatile.shared.v4.u32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"(pred),
+        "r"(a), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
+__device__ __forceinline__ void sts_v2_if(uint32_t pred, uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.volatile.shared.v2.u32 [%1], {%2, %3};\n\t}" ::"r"(pred),
+                 "r"(a), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_u32_if(uint32_t pred, uint32_t a, uint32_t x) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.volatile.shared.u32 [%1], %2;\n\t}" ::"r"(pred), "r"(a),
+                 "r"(x)
+                 : "memory");
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+
+// TIER 2 of the speculative coder (one symbol, any case; out of line, rare): as coder_tier2, the words from memory.
+__device__ __noinline__ T2Out coder_tier2_g(uint32_t res_a, uint32_t win_a, uint32_t meta_a, const float *__restrict__ scale_tab,
+                                            uint32_t ring_mask, int lane, uint32_t j, const uint4 h, uint64_t D, uint64_t R,
+                                            uint32_t w0, uint32_t wpos, const uint32_t *__restrict__ words, uint32_t wmax) {
+    const uint64_t scale = R >> 24;
+    const uint64_t P0 = scale * h.x, P1 = scale * h.y, P2 = scale * h.z, P3 = scale * h.w;
+    const bool c1 = D >= P1, c2 = D >= P2;
+    const uint64_t nlo = c2 ? P2 : (c1 ? P1 : P0);
+    const uint64_t nhi = c2 ? P3 : (c1 ? P2 : P1);
+    uint64_t Dn = D - nlo, Rn = nhi - nlo;  // (none of the three <=> Dn >= Rn: see fast_step)
+    uint32_t rw = c2 ? (CCD_WIN_HALF + 1u) : (c1 ? (uint32_t)CCD_WIN_HALF : (CCD_WIN_HALF - 1u));
+    uint32_t flags = 0u;
+    if (Dn >= Rn) {
+        const uint32_t slot = j & ring_mask;
+        const FarOut o = coder_far(win_a + slot * (CCD_WIN * 4), meta_a + slot * 16u, scale_tab, lane, scale, D);
+        Dn = D - o.lo;
+        Rn = o.hi - o.lo;
+        rw = o.rw;
+        flags = o.flags | 8u;
+    }
+    if ((Rn >> 32) == 0) {
+        Dn = (Dn << 32) | w0;
+        Rn <<= 32;
+        wpos++;
+        w0 = coder_word(words, wmax, wpos);
+    }
+    if (rw != (uint32_t)CCD_WIN_HALF) sts_u32(res_a + (j & ring_mask) * 4u, res_tag(j) | rw);
+    T2Out r;
+    r.d_lo = (uint32_t)Dn;
+    r.d_hi = (uint32_t)(Dn >> 32);
+    r.r_lo = (uint32_t)Rn;
+    r.r_hi = (uint32_t)(Rn >> 32);
+    r.w0 = w0;
+    r.wpos = wpos;
+    r.flags = flags;
+    return r;
+}
+
+// A round none of whose sequences matched: the longest decided prefix (0, 1 or 2 symbols) is taken from a lane that
+// matched it -- its state after that prefix, its result words -- and the next symbol goes through tier 2.
+struct PrefixOut {
+    uint32_t d_lo, d_hi, r_lo, r_hi, k, n;
+};
+__device__ __noinline__ PrefixOut spec_prefix(uint32_t res_a, uint32_t ring_mask, int lane, uint32_t j, uint32_t ok1,
+                                              uint32_t ok12, uint64_t d1, uint64_t r1, uint32_t k1, uint64_t d2,
+                                              uint64_t r2, uint32_t k2) {
+    PrefixOut o;
+    const uint32_t b1 = __ballot_sync(0xffffffffu, ok1 != 0u), b2 = __ballot_sync(0xffffffffu, ok12 != 0u);
+    o.n = b2 ? 2u : (b1 ? 1u : 0u);
+    o.d_lo = o.d_hi = o.r_lo = o.r_hi = o.k = 0u;
+    if (o.n) {
+        const int src = __ffs((int)(b2 ? b2 : b1)) - 1;
+        const uint64_t ds = b2 ? d2 : d1, rs = b2 ? r2 : r1;
+        o.d_lo = __shfl_sync(0xffffffffu, (uint32_t)ds, src);
+        o.d_hi = __shfl_sync(0xffffffffu, (uint32_t)(ds >> 32), src);
+        o.r_lo = __shfl_sync(0xffffffffu, (uint32_t)rs, src);
+        o.r_hi = __shfl_sync(0xffffffffu, (uint32_t)(rs >> 32), src);
+        o.k = __shfl_sync(0xffffffffu, b2 ? k2 : k1, src);
+        const uint32_t q1 = (uint32_t)src % 3u, q2 = ((uint32_t)src / 3u) % 3u;
+        if (lane == 0) {
+            if (q1 != 1u) sts_u32(res_a + (j & ring_mask) * 4u, res_tag(j) | (CCD_WIN_HALF - 1u + q1));
+            if (o.n == 2u && q2 != 1u)
+                sts_u32(res_a + ((j + 1u) & ring_mask) * 4u, res_tag(j + 1u) | (CCD_WIN_HALF - 1u + q2));
+        }
+        __syncwarp();
+    }
+    return o;
+}
+
+__device__ __forceinline__ void coder_grid_spec(const SLoc &S, const SmemLayout &sm, const float *__restrict__ scale_tab,
+                                                int lane, uint32_t ord_begin, uint32_t ord_end, DecState &c,
+                                                ProfCounters &pc) {
+    constexpr uint32_t NS = 3;  // symbols per round
+    const uint32_t ring_mask = (uint32_t)S.ring - 1u;
+    const uint32_t ready_a = sm.ctrl + 4u, done_a = sm.ctrl + 8u;
+    const uint32_t rec_a = sm.ctrl + 32u;  // record: D lo, D hi, R lo, R hi | words consumed, tag
+    const uint32_t *__restrict__ words = S.words;
+    const uint32_t wmax = (uint32_t)S.n_words + 1u;  // words[n_words .. n_words + 3] are zero (host padding)
+    uint64_t D = c.D, R = c.R;
+    uint32_t w0 = c.w0, wpos = c.wpos, w1 = 0u, w2 = 0u;
+    uint32_t j = ord_begin, limit = ord_begin;
+    // this lane's sequence: digits, the addresses of its candidates in a hot entry, its result words
+    const uint32_t c1 = (uint32_t)lane % 3u, c2 = ((uint32_t)lane / 3u) % 3u, c3 = (uint32_t)lane / 9u;
+    const uint32_t live = (uint32_t)lane < 27u ? 1u : 0u;
+    const uint32_t hb1 = sm.hot + c1 * 4u, hb2 = sm.hot + 16u + c2 * 4u, hb3 = sm.hot + 32u + (c3 < 3u ? c3 : 2u) * 4u;
+    // result word of a round, written by the matching lane at the slot of the round's FIRST symbol unless all three are
+    // the mode: value = 0x40 | the lane's number (its three digits)
+    const uint32_t CR = (1u << 10) | 0x200u | 0x40u | (uint32_t)lane;
+    const uint32_t ner = (live != 0u && lane != 13) ? 1u : 0u;
+    auto refresh = [&]() {
+        const uint32_t r = lds_acq_u32(ready_a);
+        limit = ((int32_t)(r - ord_end) > 0) ? ord_end : r;
+    };
+    // the words a round may shift in come from REGISTERS: lane l holds word[wbase + l]; the window moves (one global
+    // load per lane) when fewer than 8 words are left in it -- two rounds take at most 6 and look 2 ahead
+    uint32_t wcur = c.wcur, wbase = c.wbase;
+    auto move_window = [&]() {
+        wbase = wpos;
+        wcur = coder_word(words, wmax, wbase + (uint32_t)lane);
+    };
+    auto load_words = [&]() {
+        const uint32_t t = wpos - wbase;
+        w0 = __shfl_sync(0xffffffffu, wcur, (int)t);
+        w1 = __shfl_sync(0xffffffffu, wcur, (int)(t + 1u));
+        w2 = __shfl_sync(0xffffffffu, wcur, (int)(t + 2u));
+    };
+    auto note_flags = [&](uint32_t fl) {
+        if (fl & 2u) c.slow++;
+        if (fl & 4u) c.err = CCD_ERR_DESYNC;
+#ifdef CCD_PROFILE
+        c.n_far++;
+#endif
+    };
+    if (lane == 0) sts_v2(rec_a + 16u, make_uint2(0u, 0xffffffffu));
+    __syncwarp();
+// one step of this lane's hypothesis: [LA, LB) = its candidate's interval, WK = the word a renormalisation shifts in
+// given the renormalisations of the lane so far
+#define CCD_SSTEP(LA, LB, WK)                                                                                         \
+    {                                                                                                                 \
+        const uint32_t sl_ = __funnelshift_r(rl, rh, 24), sh_ = rh >> 24; /* scale = R >> 24 (40 bits) */             \
+        const uint32_t p_ = (LB) - (LA);                                                                              \
+        const uint64_t t_ = (uint64_t)sl_ * p_, u_ = (uint64_t)sl_ * (LA);                                            \
+        const uint32_t nl_ = (uint32_t)t_, nh_ = (uint32_t)(t_ >> 32) + sh_ * p_;           /* scale * prob */       \
+        const uint64_t lo_ = ((uint64_t)((uint32_t)(u_ >> 32) + sh_ * (LA)) << 32) | (uint32_t)u_; /* scale * left */ \
+        const uint64_t dn_ = (((uint64_t)dh << 32) | dl) - lo_;                                                       \
+        ok &= (dn_ < (((uint64_t)nh_ << 32) | nl_)) ? 1u : 0u;                                                        \
+        const bool small_ = nh_ == 0u;                                                                                \
+        dh = small_ ? (uint32_t)dn_ : (uint32_t)(dn_ >> 32);                                                          \
+        dl = small_ ? (WK) : (uint32_t)dn_;                                                                           \
+        rh = small_ ? nl_ : nh_;                                                                                      \
+        rl = small_ ? 0u : nl_;                                                                                       \
+        k += small_ ? 1u : 0u;                                                                                        \
+    }
+// entries of the round that starts at symbol JJ, into set X
+#define CCD_SLOAD(X, JJ)                                                                                              \
+    {                                                                                                                 \
+        const uint32_t so_ = ((JJ) & ring_mask) << 4; /* (the ring's first entries are mirrored behind its end) */     \
+        X##a1 = lds_u32(hb1 + so_), X##b1 = lds_u32(hb1 + so_ + 4u);                                                  \
+        X##a2 = lds_u32(hb2 + so_), X##b2 = lds_u32(hb2 + so_ + 4u);                                                  \
+        X##a3 = lds_u32(hb3 + so_), X##b3 = lds_u32(hb3 + so_ + 4u);                                                  \
+    }
+// one round on set X; failed != 0 afterwards when no sequence matched (state advanced over the decided prefix)
+// (shared-memory accesses of one warp are performed in program order: the record is read back without a barrier)
+#ifdef CCD_SPEC_SYNCWARP
+#define CCD_SPEC_SYNC() __syncwarp()
+#else
+#define CCD_SPEC_SYNC()
+#endif
+#define CCD_RSTEPS(X)                                                                                                 \
+        uint32_t dl = (uint32_t)D, dh = (uint32_t)(D >> 32), rl = (uint32_t)R, rh = (uint32_t)(R >> 32);              \
+        uint32_t ok = live, k = 0u;                                                                                   \
+        CCD_SSTEP(X##a1, X##b1, w0)                                                                                   \
+        const uint32_t dl1_ = dl, dh1_ = dh, rl1_ = rl, rh1_ = rh, k1_ = k, ok1_ = ok;                                \
+        const uint32_t wk2_ = k ? w1 : w0;                                                                            \
+        CCD_SSTEP(X##a2, X##b2, wk2_)                                                                                 \
+        const uint32_t dl2_ = dl, dh2_ = dh, rl2_ = rl, rh2_ = rh, k2_ = k, ok12_ = ok;                               \
+        const uint32_t wk3_ = (k & 2u) ? w2 : ((k & 1u) ? w1 : w0);                                                   \
+        CCD_SSTEP(X##a3, X##b3, wk3_)                                                                                 \
+        const uint32_t tag_ = j + NS;                                                                                 \
+        /* the matching lane: the result word of the round, then the record (program order) */                       \
+        sts_u32_if(ok & ner, sm.res + ((j & ring_mask) << 2), (j << 10) + CR);                                        \
+        sts_v4_if(ok, rec_a, dl, dh, rl, rh);                                                                         \
+        sts_v2_if(ok, rec_a + 16u, k, tag_);                                                                          \
+        CCD_SPEC_SYNC();                                                                                              \
+        const uint4 rv_ = lds_v4(rec_a);                                                                              \
+        const uint2 rt_ = lds_v2(rec_a + 16u);
+// (the three macros share the names the steps define)
+#define CCD_MATCHED() (rt_.y == tag_)
+#define CCD_ACCEPT()                                                                                                  \
+    {                                                                                                                 \
+        D = ((uint64_t)rv_.y << 32) | rv_.x;                                                                          \
+        R = ((uint64_t)rv_.w << 32) | rv_.z;                                                                          \
+        wpos += rt_.x;                                                                                                \
+        j = tag_;                                                                                                     \
+        sts_done(done_a, j);                                                                                          \
+        load_words();                                                                                                 \
+        PROF_COUNT_OK();                                                                                              \
+    }
+// no sequence matched: the decided prefix, then the symbol outside {M-1, M, M+1} through tier 2
+#define CCD_FAILED()                                                                                                  \
+    {                                                                                                                 \
+        const PrefixOut po_ = spec_prefix(sm.res, ring_mask, lane, j, ok1_, ok12_, ((uint64_t)dh1_ << 32) | dl1_,     \
+                                          ((uint64_t)rh1_ << 32) | rl1_, k1_, ((uint64_t)dh2_ << 32) | dl2_,          \
+                                          ((uint64_t)rh2_ << 32) | rl2_, k2_);                                        \
+        if (po_.n) {                                                                                                  \
+            D = ((uint64_t)po_.d_hi << 32) | po_.d_lo;                                                                \
+            R = ((uint64_t)po_.r_hi << 32) | po_.r_lo;                                                                \
+            wpos += po_.k;                                                                                            \
+            j += po_.n;                                                                                               \
+        }                                                                                                             \
+        {                                                                                                             \
+            const uint4 hh_ = lds_v4(sm.hot + (j & ring_mask) * 16u);                                                 \
+            const uint32_t wj_ = __shfl_sync(0xffffffffu, wcur, (int)(wpos - wbase));                                 \
+            const T2Out t2_ = coder_tier2_g(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, j, hh_, D, R, wj_, wpos, \
+                                            words, wmax);                                                             \
+            D = ((uint64_t)t2_.d_hi << 32) | t2_.d_lo;                                                                \
+            R = ((uint64_t)t2_.r_hi << 32) | t2_.r_lo;                                                                \
+            wpos = t2_.wpos;                                                                                          \
+            if (t2_.flags != 0u) note_flags(t2_.flags);                                                               \
+        }                                                                                                             \
+        j++;                                                                                                          \
+        sts_done(done_a, j);                                                                                          \
+        if (wpos - wbase >= 24u) move_window();                                                                       \
+        load_words();                                                                                                 \
+        PROF_COUNT_FAIL(po_.n);                                                                                       \
+    }
+#ifdef CCD_PROFILE
+#define PROF_COUNT_FAIL(N) do { pc.seg[3] += (N); c.n_redo++; } while (0)
+#define PROF_COUNT_OK() do { pc.seg[3] += NS; } while (0)
+#else
+#define PROF_COUNT_FAIL(N)
+#define PROF_COUNT_OK()
+#endif
+    uint32_t pa1, pb1, pa2, pb2, pa3, pb3, qa1, qb1, qa2, qb2, qa3, qb3;  // two sets of candidate intervals
+    while (j != ord_end) {
+        if ((int32_t)(limit - j) <= 0) {
+            PROF_T(t0);
+            do {
+                refresh();
+            } while ((int32_t)(limit - j) <= 0);
+            PROF_ADD(pc.wait, t0);
+        }
+        if ((int32_t)(limit - j) < (int32_t)NS) {
+            // one symbol: tier-1 test, tier 2 through the function (short diagonals)
+            const uint4 hh = lds_v4(sm.hot + (j & ring_mask) * 16u);
+            {
+                const uint64_t scale_ = R >> 24;
+                const uint64_t lo_ = scale_ * hh.y, rn_ = scale_ * (hh.z - hh.y);
+                const uint64_t dn_ = D - lo_;
+                if ((uint32_t)(dn_ >> 32) < (uint32_t)(rn_ >> 32)) {
+                    D = dn_;
+                    R = rn_;
+                } else {
+                    const T2Out r_ = coder_tier2_g(sm.res, sm.win, sm.meta, scale_tab, ring_mask, lane, j, hh, D, R, w0, wpos,
+                                                   words, wmax);
+                    D = ((uint64_t)r_.d_hi << 32) | r_.d_lo;
+                    R = ((uint64_t)r_.r_hi << 32) | r_.r_lo;
+                    w0 = r_.w0;
+                    wpos = r_.wpos;
+                    if (__builtin_expect(r_.flags != 0u, 0)) note_flags(r_.flags);
+                }
+            }
+            j++;
+            sts_done(done_a, j);
+#ifdef CCD_PROFILE
+            pc.seg[4]++;
+#endif
+            continue;
+        }
+        if (wpos - wbase >= 24u) move_window();
+        load_words();
+        CCD_SLOAD(p, j)
+        if ((int32_t)(limit - j) < (int32_t)(3u * NS)) {
+            // fewer symbols ready than the steady loop wants: one round
+            CCD_RSTEPS(p)
+            if (CCD_MATCHED()) CCD_ACCEPT() else CCD_FAILED()
+            continue;
+        }
+        // ---- steady state: two rounds per iteration, the two sets of intervals swapping roles (no copies); the
+        // intervals of the next round are requested before the steps of the current one.  The common path is the
+        // fall-through all the way to the back-edge (a taken branch costs this warp 10 ... 40 cycles).
+        while (true) {
+            if (((int32_t)(limit - j) < (int32_t)(3u * NS)) | (wpos - wbase >= 24u)) {  // (two rare cases, one test)
+                if (wpos - wbase >= 24u) {
+                    move_window();
+                    load_words();
+                }
+                if ((int32_t)(limit - j) < (int32_t)(3u * NS)) {
+                    refresh();
+                    if ((int32_t)(limit - j) < (int32_t)(3u * NS)) break;
+                }
+            }
+            CCD_SLOAD(q, j + NS)
+            {
+                CCD_RSTEPS(p)
+                if (__builtin_expect(CCD_MATCHED(), 1)) {
+                    CCD_ACCEPT()
+                    CCD_SLOAD(p, j + NS)
+                    {
+                        CCD_RSTEPS(q)
+                        if (__builtin_expect(CCD_MATCHED(), 1)) {
+                            CCD_ACCEPT()
+                            continue;
+                        }
+                        CCD_FAILED()
+                        CCD_SLOAD(p, j)
+                        continue;
+                    }
+                }
+                CCD_FAILED()
+                CCD_SLOAD(p, j)
+            }
+        }
+    }
+#undef CCD_SSTEP
+#undef CCD_SLOAD
+#undef CCD_RSTEPS
+#undef CCD_MATCHED
+#undef CCD_ACCEPT
+#undef CCD_FAILED
+    c.D = D;
+    c.R = R;
+    c.w0 = w0;
+    c.wpos = wpos;
+    c.wcur = wcur;
+    c.wbase = wbase;
+}
+
 // Helper warp: readiness scan + publication, 32 symbols per round (lane = symbol).
 __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm, int lane, uint32_t ord_begin,
                                             uint32_t ord_end, ProfCounters &pc) {
@@ -1150,15 +1498,27 @@ __device__ __forceinline__ void helper_grid(const SLoc &S, const SmemLayout &sm,
             if ((uint32_t)lane < cnt) {
                 const uint32_t jj = p + (uint32_t)lane;
                 const uint32_t slot = jj & ring_mask;
-                const uint32_t w = lds_u32(sm.res + slot * 4u);
+                const uint32_t ra = sm.res + slot * 4u;
+                const uint32_t w = lds_u32(ra);
                 const uint4 m = lds_v4(sm.meta + slot * 16u);
-                const bool other = (w & 0x7fffff00u) == res_tag(jj);
                 const int base = (int)(m.y >> 16) - 128;  // s_lo
                 int sym = base + CCD_WIN_HALF;
-                if (other) {
-                    const int v = (int)(w & 0xffu);
-                    sym = (w >> 31) ? (int)(int8_t)v : base + v;
-                    sts_u32(sm.res + slot * 4u, 0u);  // no stale word survives a trip around the ring
+                if ((w & 0xfffffe00u) == res_tag(jj)) {
+                    const uint32_t v = w & 0x1ffu;
+                    if (v & 0x100u) sym = (int)(int8_t)(v & 0xffu);                                    // the symbol itself
+                    else if ((v & 0xc0u) == 0x40u) sym = base + (int)(CCD_WIN_HALF - 1u + (v & 0x3fu) % 3u);  // first of a round
+                    else sym = base + (int)v;                                                          // window index
+                    if ((v & 0x1c0u) != 0x40u) sts_u32(ra, 0u);  // no stale word survives a trip around the ring
+                } else {
+                    // second or third symbol of a round whose word sits one or two slots back?
+                    const uint32_t ra1 = sm.res + ((jj - 1u) & ring_mask) * 4u, ra2 = sm.res + ((jj - 2u) & ring_mask) * 4u;
+                    const uint32_t w1 = lds_u32(ra1), w2 = lds_u32(ra2);
+                    if ((w1 & 0xffffffc0u) == (res_tag(jj - 1u) | 0x40u))
+                        sym = base + (int)(CCD_WIN_HALF - 1u + ((w1 & 0x3fu) / 3u) % 3u);
+                    else if ((w2 & 0xffffffc0u) == (res_tag(jj - 2u) | 0x40u)) {
+                        sym = base + (int)(CCD_WIN_HALF - 1u + (w2 & 0x3fu) / 9u);
+                        sts_u32(ra2, 0u);  // (the last reader of the round's word)
+                    }
                 }
                 sts_u8(sm.rows + (m.y & 0xffffu), sym);
                 S.latents[m.x] = (int8_t)sym;
@@ -1276,6 +1636,7 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
         sts_v4(sm.meta + 16u * i, make_uint4(0, 0, 0, 0));
         sts_u32(sm.res + 4u * i, 0u);
     }
+    if (atid < (int)CCD_RES_MIRROR) sts_u32(sm.res + 4u * (uint32_t)(S.ring + atid), 0u);
     for (int i = atid * 4; i < G.arm_blob_bytes; i += n_active * 4)
         *reinterpret_cast<uint32_t *>(sm.arm + i) = *reinterpret_cast<const uint32_t *>(G.blob + i);
 
@@ -1320,7 +1681,11 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
         const uint32_t n_sym = (uint32_t)sm.grid->h * (uint32_t)sm.grid->w;
         PROF_T(tg);
         if (is_coder) {
+#ifdef CCD_CODER_BLOCKS
             if (S.mode == 0) coder_grid(S, sm, scale_tab, lane, ord, ord + n_sym, ds, pc);
+#else
+            if (S.mode == 0) coder_grid_spec(S, sm, scale_tab, lane, ord, ord + n_sym, ds, pc);
+#endif
             else if (S.mode == 1) encode_grid<1>(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
             else encode_grid<2>(S, sm, scale_tab, lane, ord, ord + n_sym, cd);
         } else if (is_helper) {
@@ -1401,7 +1766,7 @@ unsigned long long g_ccd_launches = 0;
 
 size_t ccd_entropy_smem_bytes(int ring, int rows, int arm_blob_bytes, int ifce_blob_max) {
     size_t p = 64 + align16(sizeof(EntGrid)) + align16((size_t)arm_blob_bytes) + align16((size_t)ifce_blob_max);
-    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)(ring + CCD_HOT_MIRROR) * 16 + (size_t)ring * 4 +
+    p += 16 + (size_t)ring * 16 + (size_t)ring * CCD_WIN * 4 + (size_t)(ring + CCD_HOT_MIRROR) * 16 + (size_t)(ring + 4) * 4 +
          (size_t)rows * CCD_ROW_COLS;
     return p;
 }
