@@ -634,10 +634,6 @@ struct Coder {          // range ENcoder state
     uint32_t slow;       // symbols outside the window
 };
 
-__device__ __forceinline__ uint32_t load_word(const SLoc &S, int64_t i) {
-    return (i < S.n_words) ? __ldg(S.words + i) : 0u;
-}
-
 // Exhaustive search with the exact f64 model for a symbol outside the 31-symbol window.
 // q: quantile (uniform).  Returns {l0, l1, src, sym}: per-lane cumulatives of the lane's
 // candidate in the winning round, the winning lane and the symbol.  (Returned in registers:
@@ -693,14 +689,15 @@ __device__ __noinline__ void encoder_emit(const SLoc &S, Coder &c, uint32_t L0, 
 
 // =======================================================================================
 // Range DEcoder = two warps.
-//   coder  (warp 15): only the (D, R) recursion, executed identically by all its lanes: a
-//          scalar most-probable-first search over the 8 cumulatives around the mode (two
-//          broadcast LDS.128, prefetched), pure 64-bit integer ALU on the serial chain.
-//          (Measured on B200: every vote / shuffle / shared-memory round trip costs 27-35
-//          cycles, a dependent ALU op ~5: lane-parallel candidate evaluation loses.)
+//   coder  (warp 15): only the (D, R) recursion.  Its lanes enumerate SEQUENCES of the next three symbols and run
+//          the exact recursion each on its own hypothesis; one shared-memory record round trip per three symbols
+//          hands the matching lane's state to all of them (coder_grid_spec below; the design it replaced -- all
+//          lanes executing one scalar chain, blocks of four "is it the mode?" steps -- is kept behind
+//          -DCCD_CODER_BLOCKS for A/B measurements).  Measured on B200: a vote / shuffle / shared-memory round trip
+//          costs this warp 27-35 cycles, a dependent ALU op 4-5, a taken branch 10-45.
 //   helper (warp 14): everything that is not on that recursion, 32 symbols at a time:
 //          finds how far the producers have got (contiguous valid tags -> `ready`), turns the
-//          coder's per-symbol results into symbols, writes the row ring / latent array and
+//          coder's result words into symbols, writes the row ring / latent array and
 //          advances `progress` for the producers.
 // ctrl words: [0] progress (symbols published), [1] ready (symbols whose window is in the ring)
 // =======================================================================================
@@ -740,7 +737,8 @@ __device__ __forceinline__ uint32_t word_at(uint32_t wcur, uint32_t wnxt, uint32
 __device__ __forceinline__ uint32_t res_tag(uint32_t j) { return ((j + 1u) << 10) | 0x200u; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The recursion, two tiers (cycle figures: tools/ubench/steps.cu on a B200, one warp):
+// The scalar recursion, two tiers (cycle figures: tools/ubench/steps.cu on a B200, one warp).  TIER 2 and the far
+// path serve both coders (the symbol no sequence matched / short diagonals); the blocks of TIER 1 only the block coder.
 //
 // TIER 1 -- "is it the mode?", branch-free, K symbols per branch.  h = (left(M-1), left(M), left(M+1), left(M+2))
 //   of the most probable symbol M.  With scale = R >> 24, lo = scale * left(M), rn = scale * p(M), Dn = D - lo:
@@ -823,6 +821,7 @@ struct T2Out {
     uint32_t d_lo, d_hi, r_lo, r_hi, w0, wpos;
     uint32_t flags;  // 2: outside the window (exact search), 4: desynchronised, 8: far (instrumented build)
 };
+#ifdef CCD_CODER_BLOCKS
 __device__ __noinline__ T2Out coder_tier2(uint32_t res_a, uint32_t win_a, uint32_t meta_a, const float *__restrict__ scale_tab,
                                           uint32_t ring_mask, int lane, uint32_t j, const uint4 h, uint64_t D, uint64_t R,
                                           uint32_t w0, uint32_t wpos, const uint32_t wcur, const uint32_t wnxt,
@@ -1128,6 +1127,8 @@ __device__ __forceinline__ void coder_grid(const SLoc &S, const SmemLayout &sm, 
     c.wnxt = wnxt;
     c.wbase = wbase;
 }
+
+#endif  // CCD_CODER_BLOCKS
 
 // ---------------------------------------------------------------------------------------------------------------
 // SPECULATIVE coder (default): the lanes of the coder warp enumerate SYMBOL SEQUENCES.
