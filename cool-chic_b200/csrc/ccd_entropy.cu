@@ -1602,11 +1602,14 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EntStream &G = streams[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // role assignment: warp 15 = range coder (recursion), warp 14 = its helper; producer warps are
-    // those enabled in prod_mask (by default the coder keeps its scheduler partition for itself)
-    const uint32_t prod_mask = G.prod_mask & ((1u << (CCD_ENT_WARPS - 2)) - 1u);
-    const bool is_coder = (warp == CCD_ENT_WARPS - 1);
-    const bool is_helper = (warp == CCD_ENT_WARPS - 2);
+    // role assignment: the last warp = range coder (recursion), the one before = its helper; producer warps are those
+    // enabled in prod_mask (by default the coder keeps its scheduler partition for itself: warps 3, 7, 11 idle).  The
+    // CTA has 16 warps, or 8 when the call holds more streams than the GPU has SMs (two CTAs per SM then: the two coder
+    // warps share the scheduler the idle warps leave to them, each issuing ~40 % of the time)
+    const int nw = (int)(blockDim.x >> 5);
+    const uint32_t prod_mask = G.prod_mask & ((1u << (nw - 2)) - 1u);
+    const bool is_coder = (warp == nw - 1);
+    const bool is_helper = (warp == nw - 2);
     const bool is_prod = !is_coder && !is_helper && ((prod_mask >> warp) & 1u);
     if (!is_coder && !is_helper && !is_prod) return;
     const int n_prod = __popc(prod_mask);
@@ -1751,12 +1754,14 @@ __global__ void __launch_bounds__(CCD_ENT_THREADS, 1)
 }
 
 template <int NCTX, int CF, bool FAST>
-int launch_t(const EntStream *d_streams, int n, size_t smem, const uint32_t *cdf, const float *scale,
+int launch_t(const EntStream *d_streams, int n, size_t smem, int threads, const uint32_t *cdf, const float *scale,
              cudaStream_t st) {
     auto kern = k_entropy<NCTX, CF, FAST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<n, CCD_ENT_THREADS, smem, st>>>(d_streams, cdf, scale);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<n, threads, smem, st>>>(d_streams, cdf, scale);
     g_ccd_launches++;
     return (int)cudaGetLastError();
 }
@@ -1780,13 +1785,13 @@ bool ccd_entropy_has_fast(int n_ctx, int cf) {
 int ccd_entropy_launch(const EntStream *d_streams, int n_streams, const EntLaunchCfg &cfg,
                        const uint32_t *d_cdf, const float *d_scale, cudaStream_t st) {
     if (cfg.fast) {
-        if (cfg.n_ctx == 6 && cfg.cf == 2) return launch_t<6, 2, true>(d_streams, n_streams, cfg.smem_bytes, d_cdf, d_scale, st);
-        if (cfg.n_ctx == 10 && cfg.cf == 2) return launch_t<10, 2, true>(d_streams, n_streams, cfg.smem_bytes, d_cdf, d_scale, st);
-        if (cfg.n_ctx == 10 && cfg.cf == 4) return launch_t<10, 4, true>(d_streams, n_streams, cfg.smem_bytes, d_cdf, d_scale, st);
-        if (cfg.n_ctx == 14 && cfg.cf == 6) return launch_t<14, 6, true>(d_streams, n_streams, cfg.smem_bytes, d_cdf, d_scale, st);
-        if (cfg.n_ctx == 20 && cfg.cf == 6) return launch_t<20, 6, true>(d_streams, n_streams, cfg.smem_bytes, d_cdf, d_scale, st);
+        if (cfg.n_ctx == 6 && cfg.cf == 2) return launch_t<6, 2, true>(d_streams, n_streams, cfg.smem_bytes, cfg.threads, d_cdf, d_scale, st);
+        if (cfg.n_ctx == 10 && cfg.cf == 2) return launch_t<10, 2, true>(d_streams, n_streams, cfg.smem_bytes, cfg.threads, d_cdf, d_scale, st);
+        if (cfg.n_ctx == 10 && cfg.cf == 4) return launch_t<10, 4, true>(d_streams, n_streams, cfg.smem_bytes, cfg.threads, d_cdf, d_scale, st);
+        if (cfg.n_ctx == 14 && cfg.cf == 6) return launch_t<14, 6, true>(d_streams, n_streams, cfg.smem_bytes, cfg.threads, d_cdf, d_scale, st);
+        if (cfg.n_ctx == 20 && cfg.cf == 6) return launch_t<20, 6, true>(d_streams, n_streams, cfg.smem_bytes, cfg.threads, d_cdf, d_scale, st);
     }
-    return launch_t<0, 0, false>(d_streams, n_streams, cfg.smem_bytes, d_cdf, d_scale, st);
+    return launch_t<0, 0, false>(d_streams, n_streams, cfg.smem_bytes, cfg.threads, d_cdf, d_scale, st);
 }
 
 int ccd_cdf_table_build(uint32_t *d_cdf, const float *d_scale, cudaStream_t st) {

@@ -10,6 +10,7 @@
 // Entropy stage (ccd_entropy.cu): one persistent CTA per Cool-chic stream.
 // --------------------------------------------------------------------------------------
 #define CCD_ENT_THREADS 512          // <= 14 producer warps + helper warp + range-coder warp
+#define CCD_ENT_THREADS_NARROW 256   // 5 producer warps + helper + coder: two streams per SM when a call holds more streams than SMs
 #define CCD_ENT_WARPS (CCD_ENT_THREADS / 32)
 #define CCD_ENT_PRODUCERS (CCD_ENT_WARPS - 2)
 #define CCD_WIN 32                   // cumulative-window entries per symbol (31 decodable symbols)
@@ -79,6 +80,7 @@ struct EntLaunchCfg {
     int n_ctx, cf;   // template selection
     bool fast;
     size_t smem_bytes;
+    int threads;     // CCD_ENT_THREADS, or CCD_ENT_THREADS_NARROW for two CTAs per SM
 };
 
 int ccd_entropy_launch(const EntStream *d_streams, int n_streams, const EntLaunchCfg &cfg,

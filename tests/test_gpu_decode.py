@@ -321,6 +321,16 @@ def test_148_streams_every_output_checked(ctx, oracle, seed_stream):
     outs2, _ = ctx.decode_many([x[0] for x in sub], [x[1] for x in sub], [x[2] for x in sub], finish=[(8, "rgb")] * 148)
     for i in range(148):
         assert torch.equal(outs2[i], outs[i]), i
+    # more streams than SMs: the entropy kernel runs 8-warp CTAs, two per SM -- same answers, stream by stream
+    n_many = 2 * 148 + 5
+    sub = [items[i % 24] for i in range(n_many)]
+    outs3, lats3 = ctx.decode_many([x[0] for x in sub], [x[1] for x in sub], [x[2] for x in sub], want_latents=True,
+                                   finish=[(8, "rgb")] * n_many)
+    torch.cuda.synchronize()
+    for i in range(n_many):
+        got = (hashlib.sha256(lats3[i].cpu().numpy().tobytes()).hexdigest(),
+               hashlib.sha256(np.ascontiguousarray(outs3[i][0].cpu().numpy()).tobytes()).hexdigest())
+        assert got == want[i % 24], i
 
 
 # ------------------------------------------------------------------------------------------
