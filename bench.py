@@ -277,16 +277,13 @@ def main():
         return pinned["t"]
 
     def pack_to_host(frames_data, fmt):
-        """finished frames on the device -> packed uint8 samples in pinned host memory"""
-        total = 0
-        packed = [ctx.pack_frame(d, 8, fmt) for d in frames_data]
-        n = sum(int(p.numel()) for p in packed)
-        buf = pinned_buf(n)
-        for p in packed:
-            buf[total:total + p.numel()].copy_(p, non_blocking=True)
-            total += int(p.numel())
+        """finished frames on the device -> packed uint8 samples in pinned host memory (the frames of one decode_many
+        call are slices of one buffer: one packing launch and one copy for the whole batch)"""
+        packed = ctx.pack_frames(frames_data, 8, fmt)
+        n = int(packed.numel())
+        pinned_buf(n)[:n].copy_(packed, non_blocking=True)
         torch.cuda.synchronize()
-        return total
+        return n
 
     if wl["kind"] == "image":
         data0 = broadcast_byte_strings(streams, src=0, device=dev)[0] if world > 1 else streams[0]

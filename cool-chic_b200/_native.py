@@ -29,6 +29,7 @@ EXPORTS = [
     "ccd_latent_count", "ccd_decode_nn", "ccd_decode_many", "ccd_decode_coolchic", "ccd_decode_latents",
     "ccd_synthesize", "ccd_encode_latents", "ccd_finish_frame", "ccd_inter_predict", "ccd_reconstruct_frame",
     "ccd_pack_frame",
+    "ccd_pack_samples",
     "ccd_debug_laplace_domain", "ccd_debug_last_status", "ccd_debug_launch_count", "ccd_debug_set_producer_mask", "ccd_debug_set_fused_synthesis", "ccd_last_timing",
 ]
 
@@ -106,6 +107,8 @@ def load_library():
         L.ccd_reconstruct_frame.argtypes = [vp, vp, ci, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp, ci, vp, vp]
         L.ccd_pack_frame.restype = ci
         L.ccd_pack_frame.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]
+        L.ccd_pack_samples.restype = ci
+        L.ccd_pack_samples.argtypes = [vp, vp, ctypes.c_size_t, ci, ci, vp, vp]
         L.ccd_debug_laplace_domain.restype = ci
         L.ccd_debug_laplace_domain.argtypes = [vp, ci, ci, vp, vp]
         L.ccd_debug_last_status.restype = ci
@@ -190,6 +193,18 @@ class Context:
         n = len(descs)
         jobs = (CcdJob * n)()
         outs, lats = [], []
+        # all outputs are slices of ONE buffer, frame after frame, plane after plane: a batch of finished planar frames
+        # is then already in output order (pack_frames: one launch, one copy to the host for the whole batch)
+        sizes = []
+        for i in range(n):
+            d = descs[i]
+            fin = finish[i] if finish is not None else None
+            if fin is not None and fin[1] == "yuv420":
+                sizes.append(d.img_h * d.img_w + 2 * (d.img_h // 2) * (d.img_w // 2))
+            else:
+                sizes.append(d.n_out_channels * d.img_h * d.img_w)
+        slab = torch.empty((sum(sizes),), dtype=torch.float32, device=self.torch_device)
+        off = 0
         for i in range(n):
             d = descs[i]
             fin = finish[i] if finish is not None else None
@@ -200,15 +215,17 @@ class Context:
             jobs[i].latent_nbytes = len(latent_bytes[i])
             if fin is not None and fin[1] == "yuv420":
                 h, w = d.img_h, d.img_w
-                out = {"y": torch.empty((1, 1, h, w), dtype=torch.float32, device=self.torch_device),
-                       "u": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=self.torch_device),
-                       "v": torch.empty((1, 1, h // 2, w // 2), dtype=torch.float32, device=self.torch_device)}
+                ny, nc = h * w, (h // 2) * (w // 2)
+                out = {"y": slab[off:off + ny].view(1, 1, h, w),
+                       "u": slab[off + ny:off + ny + nc].view(1, 1, h // 2, w // 2),
+                       "v": slab[off + ny + nc:off + ny + 2 * nc].view(1, 1, h // 2, w // 2)}
                 jobs[i].d_out = out["y"].data_ptr()
                 jobs[i].d_out_u = out["u"].data_ptr()
                 jobs[i].d_out_v = out["v"].data_ptr()
             else:
-                out = torch.empty((1, d.n_out_channels, d.img_h, d.img_w), dtype=torch.float32, device=self.torch_device)
+                out = slab[off:off + sizes[i]].view(1, d.n_out_channels, d.img_h, d.img_w)
                 jobs[i].d_out = out.data_ptr()
+            off += sizes[i]
             if fin is not None:
                 jobs[i].finish_bitdepth = int(fin[0])
                 jobs[i].finish_type = _frame_type_code(fin[1])
@@ -385,6 +402,34 @@ class Context:
         pp = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in planes])
         _check(self._lib.ccd_pack_frame(self._h, pp, h, w, cs, int(bitdepth), sample_bytes, int(bool(interleaved)),
                                         out.data_ptr(), self._stream()))
+        return out
+
+    def pack_frames(self, frames, bitdepth: int, frame_data_type: str, sample_bytes: Optional[int] = None) -> torch.Tensor:
+        """A batch of finished frames (what decode_many returns with ``finish``) -> the planar integer samples of all
+        of them, frame after frame, in ONE device tensor.  Frames that are consecutive slices of one buffer (decode_many
+        allocates them so) are converted by a single launch; anything else falls back to one pack_frame per frame."""
+        if sample_bytes is None:
+            sample_bytes = 1 if bitdepth <= 8 else 2
+        dt = torch.uint8 if sample_bytes == 1 else torch.int16
+
+        def first_last(fr):
+            if frame_data_type == "yuv420":
+                return fr["y"], (fr["y"], fr["u"], fr["v"])
+            return fr, (fr,)
+
+        total, base, contiguous = 0, None, len(frames) > 0
+        for fr in frames:
+            head, parts = first_last(fr)
+            for t in parts:
+                if base is None:
+                    base = t.data_ptr()
+                contiguous = contiguous and t.is_contiguous() and t.dtype == torch.float32 and t.data_ptr() == base + 4 * total
+                total += t.numel()
+        if not contiguous:
+            return torch.cat([self.pack_frame(fr, bitdepth, frame_data_type, False, sample_bytes) for fr in frames])
+        out = torch.empty((total,), dtype=dt, device=self.torch_device)
+        _check(self._lib.ccd_pack_samples(self._h, ctypes.c_void_p(base), total, int(bitdepth), sample_bytes, out.data_ptr(),
+                                          self._stream()))
         return out
 
     def last_timing(self):

@@ -51,18 +51,26 @@ class BitReader:
     MAX_BYTES = 65536 + 16
 
     def __init__(self, data):
-        head = data[: self.MAX_BYTES]
-        self._v = int.from_bytes(head, "big")
-        self._n = 8 * len(head)
+        # headers are tens of bytes: start with a small window (shifting a 64 KB integer for every field is what made
+        # parsing a batch of streams slow) and widen it on demand
+        self._data = data
+        self._limit = min(len(data), self.MAX_BYTES)
+        self._load(min(self._limit, 256))
         self.pos = 0
+
+    def _load(self, n_bytes: int) -> None:
+        self._v = int.from_bytes(self._data[:n_bytes], "big")
+        self._n = 8 * n_bytes
 
     def read(self, n_bits: int, signed: bool = False) -> int:
         if n_bits == 0:
             return 0
         if self.pos + n_bits > self._n:
-            raise ValueError(
-                f"Header truncated: need {n_bits} bits at position {self.pos}, have {self._n}."
-            )
+            if self.pos + n_bits > 8 * self._limit:
+                raise ValueError(
+                    f"Header truncated: need {n_bits} bits at position {self.pos}, have {8 * self._limit}."
+                )
+            self._load(min(self._limit, max(2 * (self._n // 8), (self.pos + n_bits + 7) // 8)))
         shift = self._n - self.pos - n_bits
         raw = (self._v >> shift) & ((1 << n_bits) - 1)
         self.pos += n_bits

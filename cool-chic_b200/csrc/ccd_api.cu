@@ -1490,6 +1490,18 @@ int ccd_pack_frame(CcdContext *ctx, const float *const planes[3], int h, int w, 
     return CCD_OK;
 }
 
+int ccd_pack_samples(CcdContext *ctx, const float *d_samples, size_t n, int bitdepth, int sample_bytes, void *d_out,
+                     void *cuda_stream) {
+    if (!ctx || !d_samples || !d_out || n == 0) return fail(CCD_ERR_ARG, "bad argument");
+    if (bitdepth < 1 || bitdepth > 16 || (sample_bytes != 1 && sample_bytes != 2) || (sample_bytes == 1 && bitdepth > 8))
+        return fail(CCD_ERR_ARG, "bitdepth %d does not fit %d-byte samples", bitdepth, sample_bytes);
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail(CCD_ERR_CUDA, "cudaSetDevice failed");
+    if (ccd_pack_flat(d_samples, n, bitdepth, sample_bytes, d_out, (cudaStream_t)cuda_stream))
+        return fail(CCD_ERR_CUDA, "pack_samples launch failed");
+    return CCD_OK;
+}
+
 int ccd_debug_laplace_domain(CcdContext *ctx, int sc_lo, int sc_hi, uint32_t *out_lo, uint32_t *out_hi) {
     if (!ctx || sc_lo < 0 || sc_hi > CCD_N_SCALE || sc_lo >= sc_hi || !out_lo || !out_hi) return fail(CCD_ERR_ARG, "bad argument");
     DeviceGuard guard(ctx->device);

@@ -152,6 +152,7 @@ int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, flo
 
 int ccd_pack(const float *const planes[3], int h, int w, int cs, int bitdepth, int sample_bytes, int interleaved,
              void *d_out, cudaStream_t st);
+int ccd_pack_flat(const float *d_in, size_t n, int bitdepth, int sample_bytes, void *d_out, cudaStream_t st);
 
 // P/B reconstruction (ccd_inter.cu); returns -1 for an unsupported filter size
 struct InterLaunch {

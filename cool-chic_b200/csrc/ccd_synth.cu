@@ -1891,6 +1891,16 @@ int ccd_pack(const float *const planes[3], int h, int w, int cs, int bitdepth, i
     return (int)cudaGetLastError();
 }
 
+// n samples that already lie in output order (the planes of a batch of finished frames, one after the other)
+int ccd_pack_flat(const float *d_in, size_t n, int bitdepth, int sample_bytes, void *d_out, cudaStream_t st) {
+    const float M = (float)((1 << bitdepth) - 1);
+    const unsigned blocks = 148 * 8;
+    if (sample_bytes == 1) k_pack_planar<uint8_t><<<blocks, 256, 0, st>>>(d_in, d_in, d_in, n, 0, M, (uint8_t *)d_out);
+    else k_pack_planar<uint16_t><<<blocks, 256, 0, st>>>(d_in, d_in, d_in, n, 0, M, (uint16_t *)d_out);
+    g_ccd_launches++;
+    return (int)cudaGetLastError();
+}
+
 int ccd_finish(const float *d_in, int h, int w, int bitdepth, int data_type, float *a, float *b, float *c,
                cudaStream_t st) {
     const float M = (float)((1 << bitdepth) - 1);

@@ -195,6 +195,12 @@ int ccd_reconstruct_frame(CcdContext *ctx, const float *d_residue, int n_res_ch,
 int ccd_pack_frame(CcdContext *ctx, const float *const planes[3], int h, int w, int chroma_shift,
                    int bitdepth, int sample_bytes, int interleaved, void *d_out, void *cuda_stream);
 
+/* The same conversion for n samples that already lie in output order -- the planes of a BATCH of finished
+ * planar frames stored one after the other (what ccd_decode_many writes when the caller hands it slices
+ * of one buffer): one launch and one device-to-host copy for the whole batch instead of one per frame. */
+int ccd_pack_samples(CcdContext *ctx, const float *d_samples, size_t n, int bitdepth, int sample_bytes,
+                     void *d_out, void *cuda_stream);
+
 /* Device-side evaluation of the quantised-Laplace left cumulative for testing the f64
  * exp() agreement with the host: for sc in [sc_lo, sc_hi) and every
  * numerator index n in [0, 32641) (|d| = n/256), writes to host arrays

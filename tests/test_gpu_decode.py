@@ -459,6 +459,23 @@ def test_pack_frame(ctx, fmt, bitdepth, hw):
     if fmt != "yuv420":
         got = ctx.pack_frame(data, bitdepth, fmt, interleaved=True).cpu().numpy().view(dt)
         assert np.array_equal(got, np.stack(planes).transpose(1, 2, 0).reshape(-1).astype(dt))
+    # a batch: three copies as consecutive slices of one buffer (one launch) and as separate tensors (fallback)
+    want3 = np.concatenate([p.reshape(-1) for p in planes] * 3).astype(dt)
+    flat = torch.cat([t.reshape(-1) for t in ((data["y"], data["u"], data["v"]) if fmt == "yuv420" else (data,))] * 3)
+    n_fr = flat.numel() // 3
+    if fmt == "yuv420":
+        ny, nc = h * w, (h // 2) * (w // 2)
+        batch = [{"y": flat[i * n_fr:i * n_fr + ny].view(1, 1, h, w),
+                  "u": flat[i * n_fr + ny:i * n_fr + ny + nc].view(1, 1, h // 2, w // 2),
+                  "v": flat[i * n_fr + ny + nc:(i + 1) * n_fr].view(1, 1, h // 2, w // 2)} for i in range(3)]
+        loose = [{k: v.clone() for k, v in data.items()} for _ in range(3)]
+    else:
+        batch = [flat[i * n_fr:(i + 1) * n_fr].view(1, 3, h, w) for i in range(3)]
+        loose = [data.clone() for _ in range(3)]
+    launches = ctx.launch_count()
+    assert np.array_equal(ctx.pack_frames(batch, bitdepth, fmt).cpu().numpy().view(dt), want3)
+    assert ctx.launch_count() == launches + 1
+    assert np.array_equal(ctx.pack_frames(loose, bitdepth, fmt).cpu().numpy().view(dt), want3)
 
 
 @pytest.mark.parametrize("name,fmt", [("gop5_64x96_yuv420", "yuv420"), ("gop3_40x56_rgb", "rgb"),
