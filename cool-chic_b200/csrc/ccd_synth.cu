@@ -1136,8 +1136,10 @@ __global__ void __launch_bounds__(TS2_THREADS, 3) k_tail_syn2(const TailSynJob *
             for (int p = 0; p < 4; p++) {
                 float a = bb;
 #pragma unroll
-                for (int ci = 0; ci < CINP; ci++)
-                    if (ci < cin) a = __fmaf_rn(wv[ci], x[p][ci], a);
+                // (inputs and weights beyond cin are +0: fma(0, 0, a) == a bit for bit -- a starts from a bias that is never
+                // -0 and a sum is -0 only if both terms are --, so no per-term test: a predicate copy per FMA was a third
+                // of this loop's instructions)
+                for (int ci = 0; ci < CINP; ci++) a = __fmaf_rn(wv[ci], x[p][ci], a);
                 if (P.relu0) a = fmaxf(a, 0.0f);
 #pragma unroll
                 for (int c = 0; c < C; c++) o[p][c] = __fmaf_rn(w1v[c], a, o[p][c]);
@@ -1155,8 +1157,7 @@ __global__ void __launch_bounds__(TS2_THREADS, 3) k_tail_syn2(const TailSynJob *
                 for (int c = 0; c < C; c++) {
                     float a = sbs[c];
 #pragma unroll
-                    for (int ci = 0; ci < CINP; ci++)
-                        if (ci < P.stab_in) a = __fmaf_rn(sws[c * CINP + ci], x[p][ci], a);
+                    for (int ci = 0; ci < CINP; ci++) a = __fmaf_rn(sws[c * CINP + ci], x[p][ci], a);  // (zero-padded: as above)
                     sstab[(c * SF_TH + ty) * SF_TW + tx] = a;
                 }
             }
