@@ -318,7 +318,7 @@ def main():
             return t["entropy_ms"], t["synthesis_ms"]
 
         def e2e_step():
-            got = broadcast_byte_strings(streams, src=0, device=dev) if world > 1 else streams
+            got = broadcast_byte_strings(streams, src=0, device=dev, want=mine) if world > 1 else streams
             jobs = my_jobs(got)
             outs, _ = ctx.decode_many([j[0] for j in jobs], [j[1] for j in jobs], [j[2] for j in jobs], finish=[(8, wl["fmt"])] * len(jobs))
             h2d = ctx.last_timing()["upload_bytes"]

@@ -13,8 +13,11 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
-def broadcast_byte_strings(items: Optional[Sequence[bytes]], src: int = 0, device=None) -> List[bytes]:
-    """Every rank returns the list of byte strings held by ``src``."""
+def broadcast_byte_strings(items: Optional[Sequence[bytes]], src: int = 0, device=None,
+                           want: Optional[Sequence[int]] = None) -> List[Optional[bytes]]:
+    """Every rank returns the list of byte strings held by ``src``.  ``want`` (indices) limits what a rank turns back into
+    Python byte strings -- the other entries of the returned list are None: the whole buffer still travels (one broadcast),
+    but a rank that decodes 1 / N of a batch does not cut N / N of it into pieces."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return list(items)
     dev = device if device is not None else torch.device("cpu")
@@ -28,16 +31,30 @@ def broadcast_byte_strings(items: Optional[Sequence[bytes]], src: int = 0, devic
     if rank == src:
         lens.copy_(torch.tensor([len(b) for b in items], dtype=torch.int64))
     dist.broadcast(lens, src)
-    total = int(lens.sum().item())
+    lens_l = lens.tolist()
+    total = sum(lens_l)
     buf = torch.empty(total, dtype=torch.uint8, device=dev)
     if rank == src:
-        buf.copy_(torch.frombuffer(bytearray(b"".join(items)), dtype=torch.uint8))
+        staged = bytearray(total)  # (one copy of every item, no intermediate joined bytes object)
+        p = 0
+        for b in items:
+            staged[p:p + len(b)] = b
+            p += len(b)
+        buf.copy_(torch.frombuffer(staged, dtype=torch.uint8))
     dist.broadcast(buf, src)
-    raw = buf.cpu().numpy().tobytes()
-    out, p = [], 0
-    for ln in lens.tolist():
-        out.append(raw[p:p + ln])
-        p += ln
+    wanted = range(n) if want is None else want
+    if rank == src:  # (the source already holds the strings)
+        out: List[Optional[bytes]] = [None] * n
+        for i in wanted:
+            out[i] = items[i]
+        return out
+    raw = memoryview(buf.cpu().numpy())
+    offs = [0] * (n + 1)
+    for i, ln in enumerate(lens_l):
+        offs[i + 1] = offs[i] + ln
+    out = [None] * n
+    for i in wanted:
+        out[i] = bytes(raw[offs[i]:offs[i + 1]])
     return out
 
 

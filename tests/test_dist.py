@@ -29,7 +29,10 @@ def _worker(rank, world, port, ret):
     got = broadcast_byte_strings(items, src=0)
     mine = shard_indices(len(got), rank, world)
     merged = gather_sharded({i: len(got[i]) for i in mine}, world)
-    ret[rank] = (got == [bytes([i]) * (10 + 7 * i) for i in range(5)], mine, merged)
+    part = broadcast_byte_strings(items, src=0, want=mine)  # only this rank's share is cut out of the buffer
+    ok_part = all((part[i] == bytes([i]) * (10 + 7 * i)) if i in mine else part[i] is None for i in range(5))
+    empty = broadcast_byte_strings([b"", b"x"] if rank == 0 else None, src=0)
+    ret[rank] = (got == [bytes([i]) * (10 + 7 * i) for i in range(5)] and ok_part and empty == [b"", b"x"], mine, merged)
     dist.destroy_process_group()
 
 
