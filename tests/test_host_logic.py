@@ -258,3 +258,31 @@ def test_corrupt_coolchic_header_raises_value_error():
         c._values[key] = bad
         with pytest.raises(ValueError):
             desc_from_header(c)
+
+
+def test_bit_reader_window_grows_on_demand():
+    """The header bit reader starts with a 256-byte window (shifting a 64 KB integer per field made batch parsing slow) and
+    widens it when a read crosses the end: same values as one big integer, and a clean error on truncated data."""
+    import random
+
+    import pytest
+
+    from coolchic_b200.bitstream.header import BitReader
+
+    rng = random.Random(5)
+    data = bytes(rng.randrange(256) for _ in range(3000))
+    big, n_bits = int.from_bytes(data, "big"), 8 * len(data)
+    br, pos = BitReader(data), 0
+    while pos + 40 < n_bits:
+        n = rng.choice((1, 3, 7, 8, 13, 16, 24, 32, 37))
+        want = (big >> (n_bits - pos - n)) & ((1 << n) - 1)
+        assert br.read(n) == want, pos
+        pos += n
+    assert br.pos == pos
+    br = BitReader(data[:300])
+    br.read(8 * 290)          # one read across the first window
+    br.read(8 * 10)
+    with pytest.raises(ValueError):
+        br.read(1)
+    # signed fields: sign-magnitude, as the reference writes them
+    assert BitReader(bytes([0b10000101])).read(8, signed=True) == -5 and BitReader(bytes([0b00000101])).read(8, signed=True) == 5
