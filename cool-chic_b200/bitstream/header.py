@@ -15,6 +15,7 @@ fixed-length part (header.py:33-34).
 """
 from __future__ import annotations
 
+import functools
 import math
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -326,6 +327,7 @@ class FrameHeader(_Header):
         return out
 
 
+@functools.lru_cache(maxsize=None)
 def _q_table(module: str, kind: str):
     return tuple(2.0**s for s in Q_SHIFT_TABLE[(module, kind)])
 
