@@ -48,11 +48,21 @@ def broadcast_byte_strings(items: Optional[Sequence[bytes]], src: int = 0, devic
         for i in wanted:
             out[i] = items[i]
         return out
-    raw = memoryview(buf.cpu().numpy())
     offs = [0] * (n + 1)
     for i, ln in enumerate(lens_l):
         offs[i + 1] = offs[i] + ln
     out = [None] * n
+    if want is not None and 2 * sum(lens_l[i] for i in wanted) <= total:
+        # a small share of the buffer: one gather where the buffer lives, one copy of that share to the host
+        idx = list(wanted)
+        if idx:
+            share = torch.cat([buf[offs[i]:offs[i + 1]] for i in idx]).cpu().numpy()
+            p = 0
+            for i in idx:
+                out[i] = share[p:p + lens_l[i]].tobytes()
+                p += lens_l[i]
+        return out
+    raw = memoryview(buf.cpu().numpy())
     for i in wanted:
         out[i] = bytes(raw[offs[i]:offs[i + 1]])
     return out
